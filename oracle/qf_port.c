@@ -1,0 +1,327 @@
+/* TEST INFRASTRUCTURE ONLY -- see oracle/README.md.
+ *
+ * CPU restatement ("port") of the reference's hot-path QFunctions, written from
+ * the mathematics so that the oracle is self-contained on a box where
+ * /root/reference (and a prebuilt oracle/_ref/libref_qf.so) is absent.  It is
+ * pinned against the REAL reference functions (oracle/_ref, built from
+ * /root/reference/qfunctions/ by oracle/Makefile) and against the committed
+ * golden vectors in tests/golden/ by tests/test_oracle_qfunctions.py.
+ *
+ * Reference sources restated here:
+ *   SetupGeo   qfunctions/common.h:47-101
+ *   LinElasF   qfunctions/linElas.h:39-158     LinElasdF  qfunctions/linElas.h:163-280
+ *   HyperSSF   qfunctions/hyperSS.h:60-182     HyperSSdF  qfunctions/hyperSS.h:187-321
+ *   HyperFSF   qfunctions/hyperFS.h:147-281    HyperFSdF  qfunctions/hyperFS.h:286-464
+ *   (helpers: log1p_series hyperSS.h:43-55, log1p_series_shifted hyperFS.h:45-67,
+ *    computeDetCM1 hyperFS.h:72-80, commonFS hyperFS.h:85-142)
+ *
+ * Array conventions: a GRAD field is [deriv d][comp c][Q]
+ * (d slowest); qdata is [10][Q] = {w*detJ, dXdx row-major}; stored gradu is
+ * [comp][deriv][Q].  All functions have the libCEED user-QFunction signature.
+ */
+#include <math.h>
+
+typedef struct {
+  double nu, E;
+} PortPhysics; /* elasticity.h:30-37 Physics_private */
+
+typedef double M3[3][3];
+
+/* Voigt ordering used by the reference: (00,11,22,12,02,01) */
+static const int VJ[6] = {0, 1, 2, 1, 0, 0}, VK[6] = {0, 1, 2, 2, 2, 1};
+
+static inline void voigt_to_sym(const double v[6], M3 m) {
+  m[0][0] = v[0]; m[1][1] = v[1]; m[2][2] = v[2];
+  m[1][2] = m[2][1] = v[3];
+  m[0][2] = m[2][0] = v[4];
+  m[0][1] = m[1][0] = v[5];
+}
+
+/* physical gradient  g[c][k] = sum_m dXdx[m][k] * du_ref[c][m]   with the GRAD
+ * input laid out as in[(m*3 + c)*Q + i] */
+static inline void phys_grad(const double *ug, const M3 dXdx, int Q, int i, M3 g) {
+  for (int c = 0; c < 3; c++)
+    for (int k = 0; k < 3; k++) {
+      double s = 0;
+      for (int m = 0; m < 3; m++) s += dXdx[m][k] * ug[(m * 3 + c) * Q + i];
+      g[c][k] = s;
+    }
+}
+
+/* out[(k*3 + c)*Q + i] = sum_m dXdx[k][m] * T[c][m] * wdetJ */
+static inline void pull_back(const M3 T, const M3 dXdx, double wdetJ, int Q, int i,
+                             double *out) {
+  for (int c = 0; c < 3; c++)
+    for (int k = 0; k < 3; k++) {
+      double s = 0;
+      for (int m = 0; m < 3; m++) s += dXdx[k][m] * T[c][m] * wdetJ;
+      out[(k * 3 + c) * Q + i] = s;
+    }
+}
+
+static inline void load_qdata(const double *qd, int Q, int i, double *wdetJ, M3 dXdx) {
+  *wdetJ = qd[i];
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) dXdx[a][b] = qd[(1 + 3 * a + b) * Q + i];
+}
+
+/* ---------------------------------------------------------------- SetupGeo */
+int port_SetupGeo(void *ctx, int Q, const double *const *in, double *const *out) {
+  (void)ctx;
+  const double *J = in[0], *w = in[1];
+  double *qd = out[0];
+  for (int i = 0; i < Q; i++) {
+    /* J[d][c] = d x_c / d X_d  at in[(d*3+c)*Q+i]; the reference names J(c+1)(d+1) */
+    double Jm[3][3]; /* Jm[c][d] */
+    for (int d = 0; d < 3; d++)
+      for (int c = 0; c < 3; c++) Jm[c][d] = J[(d * 3 + c) * Q + i];
+    double A[3][3];
+    A[0][0] = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+    A[0][1] = Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2];
+    A[0][2] = Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1];
+    A[1][0] = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+    A[1][1] = Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0];
+    A[1][2] = Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2];
+    A[2][0] = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+    A[2][1] = Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1];
+    A[2][2] = Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0];
+    const double detJ = Jm[0][0] * A[0][0] + Jm[1][0] * A[0][1] + Jm[2][0] * A[0][2];
+    qd[i] = w[i] * detJ;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) qd[(1 + 3 * a + b) * Q + i] = A[a][b] / detJ;
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- linElas */
+static inline void linelas_stress(const M3 g, double E, double nu, M3 sig) {
+  double e[3][3];
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) e[a][b] = (g[a][b] + g[b][a]) / 2.;
+  const double ss = E / ((1 + nu) * (1 - 2 * nu));
+  sig[0][0] = ss * ((1 - nu) * e[0][0] + nu * e[1][1] + nu * e[2][2]);
+  sig[1][1] = ss * (nu * e[0][0] + (1 - nu) * e[1][1] + nu * e[2][2]);
+  sig[2][2] = ss * (nu * e[0][0] + nu * e[1][1] + (1 - nu) * e[2][2]);
+  /* the reference's shear term carries an extra 0.5 (linElas.h:137-139); kept */
+  sig[1][2] = sig[2][1] = ss * (1 - 2 * nu) * e[1][2] * 0.5;
+  sig[0][2] = sig[2][0] = ss * (1 - 2 * nu) * e[0][2] * 0.5;
+  sig[0][1] = sig[1][0] = ss * (1 - 2 * nu) * e[0][1] * 0.5;
+}
+
+static int linelas_common(void *ctx, int Q, const double *const *in, double *const *out) {
+  const PortPhysics *p = (const PortPhysics *)ctx;
+  for (int i = 0; i < Q; i++) {
+    double wdetJ;
+    M3 dXdx, g, sig;
+    load_qdata(in[1], Q, i, &wdetJ, dXdx);
+    phys_grad(in[0], dXdx, Q, i, g);
+    linelas_stress(g, p->E, p->nu, sig);
+    pull_back(sig, dXdx, wdetJ, Q, i, out[0]);
+  }
+  return 0;
+}
+int port_LinElasF(void *ctx, int Q, const double *const *in, double *const *out) {
+  return linelas_common(ctx, Q, in, out);
+}
+int port_LinElasdF(void *ctx, int Q, const double *const *in, double *const *out) {
+  return linelas_common(ctx, Q, in, out); /* linear: Jacobian action == residual action */
+}
+
+/* ---------------------------------------------------------------- hyperSS */
+static inline double series_log1p(double x) {
+  double y = x / (2. + x);
+  const double y2 = y * y;
+  double sum = y;
+  y *= y2; sum += y / 3;
+  y *= y2; sum += y / 5;
+  y *= y2; sum += y / 7;
+  return 2 * sum;
+}
+
+static inline void lame(const PortPhysics *p, double *TwoMu, double *mu, double *lambda) {
+  *TwoMu = p->E / (1 + p->nu);
+  *mu = *TwoMu / 2;
+  const double Kbulk = p->E / (3 * (1 - 2 * p->nu));
+  *lambda = (3 * Kbulk - *TwoMu) / 3;
+}
+
+int port_HyperSSF(void *ctx, int Q, const double *const *in, double *const *out) {
+  double TwoMu, mu, lambda;
+  lame((const PortPhysics *)ctx, &TwoMu, &mu, &lambda);
+  double *gradu = out[1];
+  for (int i = 0; i < Q; i++) {
+    double wdetJ;
+    M3 dXdx, g, sig;
+    load_qdata(in[1], Q, i, &wdetJ, dXdx);
+    phys_grad(in[0], dXdx, Q, i, g);
+    for (int c = 0; c < 3; c++)
+      for (int k = 0; k < 3; k++) gradu[(c * 3 + k) * Q + i] = g[c][k];
+    double e[3][3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) e[a][b] = (g[a][b] + g[b][a]) / 2.;
+    const double llv = series_log1p(e[0][0] + e[1][1] + e[2][2]);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) sig[a][b] = (a == b ? lambda * llv : 0.) + TwoMu * e[a][b];
+    pull_back(sig, dXdx, wdetJ, Q, i, out[0]);
+  }
+  return 0;
+}
+
+int port_HyperSSdF(void *ctx, int Q, const double *const *in, double *const *out) {
+  double TwoMu, mu, lambda;
+  lame((const PortPhysics *)ctx, &TwoMu, &mu, &lambda);
+  const double *gradu = in[2];
+  for (int i = 0; i < Q; i++) {
+    double wdetJ;
+    M3 dXdx, g, dsig;
+    load_qdata(in[1], Q, i, &wdetJ, dXdx);
+    phys_grad(in[0], dXdx, Q, i, g);
+    double de[3][3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) de[a][b] = (g[a][b] + g[b][a]) / 2.;
+    const double strain_vol = gradu[0 * Q + i] + gradu[4 * Q + i] + gradu[8 * Q + i];
+    const double lambda_bar = lambda / (1 + strain_vol);
+    const double ldt = lambda_bar * (de[0][0] + de[1][1] + de[2][2]);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) dsig[a][b] = (a == b ? ldt : 0.) + TwoMu * de[a][b];
+    pull_back(dsig, dXdx, wdetJ, Q, i, out[0]);
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- hyperFS */
+static inline double series_log1p_shifted(double x) {
+  const double left = sqrt(2.) / 2 - 1, right = sqrt(2.) - 1;
+  double sum = 0;
+  if (x < left) {
+    sum -= log(2.) / 2;
+    x = 1 + 2 * x;
+  } else if (right < x) {
+    sum += log(2.) / 2;
+    x = (x - 1) / 2;
+  }
+  double y = x / (2. + x);
+  const double y2 = y * y;
+  sum += y;
+  y *= y2; sum += y / 3;
+  y *= y2; sum += y / 5;
+  y *= y2; sum += y / 7;
+  return 2 * sum;
+}
+
+/* det(C) - 1 from 2E in Voigt form, cancellation-free polynomial */
+static inline double det_c_minus_1(const double e[6]) {
+  return e[0] * (e[1] * e[2] - e[3] * e[3]) + e[5] * (e[4] * e[3] - e[5] * e[2]) +
+         e[4] * (e[5] * e[3] - e[4] * e[1]) + e[0] + e[1] + e[2] + e[0] * e[1] +
+         e[0] * e[2] + e[1] * e[2] - e[5] * e[5] - e[4] * e[4] - e[3] * e[3];
+}
+
+/* S (2nd Piola-Kirchhoff, Voigt), C^-1 (Voigt), lambda*log(J) from grad u */
+static void fs_kinematics(double lambda, double mu, const M3 g, double Sv[6],
+                          double Civ[6], double *llnj) {
+  double e2v[6];
+  for (int m = 0; m < 6; m++) {
+    const int j = VJ[m], k = VK[m];
+    double s = g[j][k] + g[k][j];
+    for (int n = 0; n < 3; n++) s += g[n][j] * g[n][k];
+    e2v[m] = s;
+  }
+  M3 E2, C;
+  voigt_to_sym(e2v, E2);
+  const double detC_m1 = det_c_minus_1(e2v);
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) C[a][b] = E2[a][b] + (a == b ? 1. : 0.);
+  const double A[6] = {C[1][1] * C[2][2] - C[1][2] * C[2][1],
+                       C[0][0] * C[2][2] - C[0][2] * C[2][0],
+                       C[0][0] * C[1][1] - C[0][1] * C[1][0],
+                       C[0][2] * C[1][0] - C[0][0] * C[1][2],
+                       C[0][1] * C[1][2] - C[0][2] * C[1][1],
+                       C[0][2] * C[2][1] - C[0][1] * C[2][2]};
+  for (int m = 0; m < 6; m++) Civ[m] = A[m] / (detC_m1 + 1.);
+  M3 Ci;
+  voigt_to_sym(Civ, Ci);
+  *llnj = lambda * series_log1p_shifted(detC_m1) / 2.;
+  for (int m = 0; m < 6; m++) {
+    double s = (*llnj) * Civ[m];
+    for (int n = 0; n < 3; n++) s += mu * Ci[VJ[m]][n] * E2[n][VK[m]];
+    Sv[m] = s;
+  }
+}
+
+int port_HyperFSF(void *ctx, int Q, const double *const *in, double *const *out) {
+  double TwoMu, mu, lambda;
+  lame((const PortPhysics *)ctx, &TwoMu, &mu, &lambda);
+  double *gradu = out[1];
+  for (int i = 0; i < Q; i++) {
+    double wdetJ, Sv[6], Civ[6], llnj;
+    M3 dXdx, g, F, S, P;
+    load_qdata(in[1], Q, i, &wdetJ, dXdx);
+    phys_grad(in[0], dXdx, Q, i, g);
+    for (int c = 0; c < 3; c++)
+      for (int k = 0; k < 3; k++) {
+        gradu[(c * 3 + k) * Q + i] = g[c][k];
+        F[c][k] = g[c][k] + (c == k ? 1. : 0.);
+      }
+    fs_kinematics(lambda, mu, g, Sv, Civ, &llnj);
+    voigt_to_sym(Sv, S);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        double s = 0;
+        for (int m = 0; m < 3; m++) s += F[a][m] * S[m][b];
+        P[a][b] = s;
+      }
+    pull_back(P, dXdx, wdetJ, Q, i, out[0]);
+  }
+  return 0;
+}
+
+int port_HyperFSdF(void *ctx, int Q, const double *const *in, double *const *out) {
+  double TwoMu, mu, lambda;
+  lame((const PortPhysics *)ctx, &TwoMu, &mu, &lambda);
+  const double *gradu = in[2];
+  for (int i = 0; i < Q; i++) {
+    double wdetJ, Sv[6], Civ[6], llnj, dEv[6];
+    M3 dXdx, gd, g, F, S, Ci, dE, dECi, dS, dP;
+    load_qdata(in[1], Q, i, &wdetJ, dXdx);
+    phys_grad(in[0], dXdx, Q, i, gd);
+    for (int c = 0; c < 3; c++)
+      for (int k = 0; k < 3; k++) {
+        g[c][k] = gradu[(c * 3 + k) * Q + i];
+        F[c][k] = g[c][k] + (c == k ? 1. : 0.);
+      }
+    fs_kinematics(lambda, mu, g, Sv, Civ, &llnj);
+    voigt_to_sym(Sv, S);
+    voigt_to_sym(Civ, Ci);
+    for (int m = 0; m < 6; m++) {
+      double s = 0;
+      for (int n = 0; n < 3; n++)
+        s += (gd[n][VJ[m]] * F[n][VK[m]] + F[n][VJ[m]] * gd[n][VK[m]]) / 2.;
+      dEv[m] = s;
+    }
+    voigt_to_sym(dEv, dE);
+    double CiE = 0;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) CiE += Ci[a][b] * dE[a][b];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        double s = 0;
+        for (int m = 0; m < 3; m++) s += dE[a][m] * Ci[m][b];
+        dECi[a][b] = s;
+      }
+    const double llnj_m = llnj - mu;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        double s = 0;
+        for (int m = 0; m < 3; m++) s += Ci[a][m] * dECi[m][b];
+        dS[a][b] = lambda * CiE * Ci[a][b] - 2. * llnj_m * s;
+      }
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        double s = 0;
+        for (int m = 0; m < 3; m++) s += gd[a][m] * S[m][b] + F[a][m] * dS[m][b];
+        dP[a][b] = s;
+      }
+    pull_back(dP, dXdx, wdetJ, Q, i, out[0]);
+  }
+  return 0;
+}
