@@ -1,0 +1,745 @@
+// Fused matrix-free operator kernels of the /gpu/b200 backend (sm_100a, FP64).
+//
+//   y_L += E^T G^T D(q-data) G E x_L          one launch per CeedOperatorApply
+//
+// replaces, for the residual / Jacobian operators the reference builds in
+// /root/reference/src/setuplibceed.c:518-542 and :818-839, the whole backend side of
+// CeedOperatorApply called from ApplyLocalCeedOp (/root/reference/src/matops.c:46):
+// offsets gather, tensor-product gradient, QFunction, transposed gradient, scatter-add.
+//
+// Mapping.  Q*Q threads per element, EB elements per CTA (EB*Q*Q ~ 128 threads).  A thread
+// always owns one LINE of the Q^3 (or P^3) lattice in registers and contracts it against the
+// basis matrix, which is a kernel parameter (constant bank, immediate operand of DFMA): one
+// LDS/STS per five DFMAs instead of one per DFMA.  Between stages the lattice is re-oriented
+// through shared memory:
+//
+//   gather (z-lines)  --B_z-->  y-lines --B_y-->  x-lines --B_x--> u~ at quadrature points
+//   x-lines: d/dx in registers;  y-lines, z-lines: d/dy, d/dz with the collocated
+//   derivative matrix Gc (Gc B = D);  x-lines again: QFunction at the thread's Q points,
+//   streaming the q-blocked per-point data straight from HBM (fully coalesced);
+//   then the exact transpose back to z-lines and an atomic scatter-add.
+//
+// FP64 work at P=Q=5: 12 line stages x 1875 DFMA + 125 x ~105 (hyperFS Jacobian from the
+// Jacobian cache) ~ 36 k per element, vs ~100 k for libCEED-style 9-contraction gradients
+// around the unmodified QFunction.  See DESIGN.md for the roofline arithmetic.
+#include "b200_qf.cuh"
+
+namespace b200 {
+
+template <int P, int Q> struct Mats {
+  double B[Q * P];   // interp1d  [Q][P]
+  double Gc[Q * Q];  // collocated derivative at the quadrature points, Gc * B = grad1d
+};
+
+template <int Q> struct Cfg {
+  static constexpr int T = Q * Q;
+  static constexpr int EB = elems_per_block(Q);
+  static constexpr int NT = ((T * EB + 31) / 32) * 32;
+  static constexpr int Q3 = Q * Q * Q;
+  static constexpr int SE = 9 * Q3 + ((9 * Q3) % 2 == 0 ? 1 : 2);  // odd element stride
+  static constexpr size_t SMEM = (size_t)EB * SE * sizeof(double);
+};
+
+#define IDX(c, x, y, z) ((c) * Q3 + ((z) * Q + (y)) * Q + (x))
+
+enum { MODE_RESIDUAL = 0, MODE_JACOBIAN = 1 };
+
+template <int P, int Q, int PROB, int MODE>
+__global__ void __launch_bounds__(Cfg<Q>::NT)
+k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
+              const int *__restrict__ offsets, const double *__restrict__ qa,
+              double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y) {
+  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
+  constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10;
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int eb = tid / T, t = tid - eb * T, a = t % Q, b = t / Q;
+  const int blk = blockIdx.x;
+  const int rem = nelem - blk * EB;
+  const int ebn = rem < EB ? rem : EB;
+  const bool act = eb < ebn;
+  const int e = blk * EB + eb;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * Q3, *R2 = R1 + 3 * Q3;
+
+  // ---- phase 0: gather node z-lines, contract z with B
+  if (act && a < P && b < P) {
+    double r[3][P];
+    const int *off = offsets + (size_t)e * P3 + b * P + a;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+      const int o = __ldg(off + k * P * P);
+#pragma unroll
+      for (int c = 0; c < 3; c++) r[c][k] = __ldg(x + o + c);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int qz = 0; qz < Q; qz++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < P; k++) s += m.B[qz * P + k] * r[c][k];
+        R0[IDX(c, a, b, qz)] = s;
+      }
+  }
+  __syncthreads();
+  // ---- phase 1: y-lines (a = i, b = qz), contract y with B
+  if (act && a < P) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[P];
+#pragma unroll
+      for (int j = 0; j < P; j++) in[j] = R0[IDX(c, a, j, b)];
+#pragma unroll
+      for (int qy = 0; qy < Q; qy++) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < P; j++) s += m.B[qy * P + j] * in[j];
+        R1[IDX(c, a, qy, b)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: x-lines (a = qy, b = qz), contract x with B; d/dx in registers
+  double Hx[3][Q];
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[P], ut[Q];
+#pragma unroll
+      for (int i = 0; i < P; i++) in[i] = R1[IDX(c, i, a, b)];
+#pragma unroll
+      for (int qx = 0; qx < Q; qx++) {
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++) s += m.B[qx * P + i] * in[i];
+        ut[qx] = s;
+        R0[IDX(c, qx, a, b)] = s;
+      }
+#pragma unroll
+      for (int qx = 0; qx < Q; qx++) {
+        double s = 0;
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[qx * Q + mm] * ut[mm];
+        Hx[c][qx] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: y-lines (a = qx, b = qz): d/dy -> R1;  phase 4: z-lines (a = qx, b = qy): d/dz -> R2
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[Q];
+#pragma unroll
+      for (int mm = 0; mm < Q; mm++) in[mm] = R0[IDX(c, a, mm, b)];
+#pragma unroll
+      for (int qy = 0; qy < Q; qy++) {
+        double s = 0;
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[qy * Q + mm] * in[mm];
+        R1[IDX(c, a, qy, b)] = s;
+      }
+#pragma unroll
+      for (int mm = 0; mm < Q; mm++) in[mm] = R0[IDX(c, a, b, mm)];
+#pragma unroll
+      for (int qz = 0; qz < Q; qz++) {
+        double s = 0;
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[qz * Q + mm] * in[mm];
+        R2[IDX(c, a, b, qz)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 5: QFunction at the Q points of this x-line; phase 6: d/dx^T in registers
+  if (act) {
+    double Wx[3][Q];
+    const size_t gb = (size_t)blk * EB * NC * Q3 + tid;
+    const size_t ebt = (size_t)ebn * T;
+#pragma unroll
+    for (int qx = 0; qx < Q; qx++) {
+      double qd[NC], H[3][3], W[3][3];
+#pragma unroll
+      for (int n = 0; n < NC; n++) qd[n] = __ldcs(qa + gb + (size_t)(n * Q + qx) * ebt);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        H[c][0] = Hx[c][qx];
+        H[c][1] = R1[IDX(c, qx, a, b)];
+        H[c][2] = R2[IDX(c, qx, a, b)];
+      }
+      if (MODE == MODE_JACOBIAN) {
+        jacobian_point<PROB>(mt, qd, H, W);
+      } else {
+        double A[3][3], g[3][3];
+#pragma unroll
+        for (int mm = 0; mm < 3; mm++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) A[mm][k] = qd[1 + 3 * mm + k];
+        if (PROB == B200_PROB_LINELAS) {
+          linelas_point(mt, qd[0], A, H, W);
+        } else {
+          if (PROB == B200_PROB_HYPERSS) hyperss_f_point(mt, qd[0], A, H, g, W);
+          else hyperfs_f_point(mt, qd[0], A, H, g, W);
+          const size_t gg = (size_t)blk * EB * 9 * Q3 + tid;
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) __stcs(gradu + gg + (size_t)((c * 3 + k) * Q + qx) * ebt, g[c][k]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        Wx[c][qx] = W[c][0];
+        R1[IDX(c, qx, a, b)] = W[c][1];
+        R2[IDX(c, qx, a, b)] = W[c][2];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int qx = 0; qx < Q; qx++) {
+        double s = 0;
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[mm * Q + qx] * Wx[c][mm];
+        R0[IDX(c, qx, a, b)] = s;
+      }
+  }
+  __syncthreads();
+  // ---- phase 7: y-lines (a = qx, b = qz): R0 += Gc^T_y Wy
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[Q];
+#pragma unroll
+      for (int mm = 0; mm < Q; mm++) in[mm] = R1[IDX(c, a, mm, b)];
+#pragma unroll
+      for (int qy = 0; qy < Q; qy++) {
+        double s = R0[IDX(c, a, qy, b)];
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[mm * Q + qy] * in[mm];
+        R0[IDX(c, a, qy, b)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 8: z-lines (a = qx, b = qy): v~ = R0 + Gc^T_z Wz, then B^T along z -> R1
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[Q], vt[Q];
+#pragma unroll
+      for (int mm = 0; mm < Q; mm++) in[mm] = R2[IDX(c, a, b, mm)];
+#pragma unroll
+      for (int qz = 0; qz < Q; qz++) {
+        double s = R0[IDX(c, a, b, qz)];
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[mm * Q + qz] * in[mm];
+        vt[qz] = s;
+      }
+#pragma unroll
+      for (int k = 0; k < P; k++) {
+        double s = 0;
+#pragma unroll
+        for (int qz = 0; qz < Q; qz++) s += m.B[qz * P + k] * vt[qz];
+        R1[IDX(c, a, b, k)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 9: y-lines (a = qx, b = k < P): B^T along y -> R2
+  if (act && b < P) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[Q];
+#pragma unroll
+      for (int qy = 0; qy < Q; qy++) in[qy] = R1[IDX(c, a, qy, b)];
+#pragma unroll
+      for (int j = 0; j < P; j++) {
+        double s = 0;
+#pragma unroll
+        for (int qy = 0; qy < Q; qy++) s += m.B[qy * P + j] * in[qy];
+        R2[IDX(c, a, j, b)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 10: x-lines (a = j < P, b = k < P): B^T along x, scatter-add
+  if (act && a < P && b < P) {
+    const int *off = offsets + (size_t)e * P3 + (b * P + a) * P;
+    int o[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) o[i] = __ldg(off + i);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double in[Q];
+#pragma unroll
+      for (int qx = 0; qx < Q; qx++) in[qx] = R2[IDX(c, qx, a, b)];
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        double s = 0;
+#pragma unroll
+        for (int qx = 0; qx < Q; qx++) s += m.B[qx * P + i] * in[qx];
+        atomicAdd(y + o[i] + c, s);
+      }
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------
+// Jacobian cache build: point-wise over the q-blocked layout (same position in every
+// component plane), coalesced.
+// -----------------------------------------------------------------------------------
+template <int PROB>
+__global__ void k_jcache_build(int nelem, int Q, const double *__restrict__ qdata,
+                               const double *__restrict__ gradu, double *__restrict__ jc) {
+  constexpr int NJ = JCache<PROB>::N;
+  const int EB = elems_per_block(Q), Q3 = Q * Q * Q, T = Q * Q;
+  const size_t npts = (size_t)nelem * Q3;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npts; i += (size_t)gridDim.x * blockDim.x) {
+    // i enumerates positions group by group: i = g*EB*Q3 + r, r in [0, ebn*Q3)
+    const size_t g = i / ((size_t)EB * Q3);
+    const int r = (int)(i - g * EB * Q3);
+    const long long rem = (long long)nelem - (long long)g * EB;
+    const int ebn = rem < EB ? (int)rem : EB;
+    const size_t plane = (size_t)ebn * T * Q;  // points per component plane in this group
+    double qd[10], gu[9], out[NJ];
+    const double *qp = qdata + g * EB * 10 * Q3 + r;
+#pragma unroll
+    for (int n = 0; n < 10; n++) qd[n] = __ldcs(qp + n * plane);
+    if (PROB != B200_PROB_LINELAS) {
+      const double *gp = gradu + g * EB * 9 * Q3 + r;
+#pragma unroll
+      for (int n = 0; n < 9; n++) gu[n] = __ldcs(gp + n * plane);
+    }
+    jcache_point<PROB>(qd, gu, out);
+    double *jp = jc + g * EB * NJ * Q3 + r;
+#pragma unroll
+    for (int n = 0; n < NJ; n++) jp[n * plane] = out[n];
+  }
+}
+
+// -----------------------------------------------------------------------------------
+// Operator diagonal (CeedOperatorLinearAssembleDiagonal, matops.c:227; App. B.5):
+//   diag_e[c][n] = sum_q sum_{d,d'} G_d[q,n] Aq_c[d'][d] G_d'[q,n],
+//   Aq_c[d'][d] = dW[c][d]/dH[c][d']  (unit inputs through the Jacobian point function)
+// G_d = Kronecker(B or D per axis) so each (d,d') term is a 3-stage sum-factorised
+// contraction with the element-wise products B.B, B.D, D.D.
+// -----------------------------------------------------------------------------------
+template <int P, int Q> struct DiagMats {
+  double M[3][Q * P];  // [0] B.B  [1] B.D  [2] D.D   (element-wise, [Q][P])
+};
+
+template <int P, int Q, int PROB>
+__global__ void __launch_bounds__(Cfg<Q>::NT)
+k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ Material mt, int nelem,
+             const int *__restrict__ offsets, const double *__restrict__ jcp, double *__restrict__ diag) {
+  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
+  constexpr int NC = JCache<PROB>::N;
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int eb = tid / T, t = tid - eb * T, a = t % Q, b = t / Q;
+  const int blk = blockIdx.x;
+  const int rem = nelem - blk * EB;
+  const int ebn = rem < EB ? rem : EB;
+  const bool act = eb < ebn;
+  const int e = blk * EB + eb;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * Q3;
+  const size_t gb = (size_t)blk * EB * NC * Q3 + tid;
+  const size_t ebt = (size_t)ebn * T;
+
+  for (int c = 0; c < 3; c++) {
+    double acc[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) acc[k] = 0;
+#pragma unroll 1
+    for (int dp = 0; dp < 3; dp++) {  // d' : direction of the unit input
+      // x-lines (a = qy, b = qz): evaluate Aq_c[d'][d] at this line's points, contract x
+      if (act) {
+        double Aq[3][Q];
+#pragma unroll
+        for (int qx = 0; qx < Q; qx++) {
+          double qd[NC], H[3][3], W[3][3];
+#pragma unroll
+          for (int n = 0; n < NC; n++) qd[n] = __ldg(jcp + gb + (size_t)(n * Q + qx) * ebt);
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) H[i][j] = (i == c && j == dp) ? 1. : 0.;
+          jacobian_point<PROB>(mt, qd, H, W);
+#pragma unroll
+          for (int d = 0; d < 3; d++) Aq[d][qx] = c == 0 ? W[0][d] : (c == 1 ? W[1][d] : W[2][d]);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const int sel = (d == 0) + (dp == 0);
+#pragma unroll
+          for (int i = 0; i < P; i++) {
+            double s = 0;
+#pragma unroll
+            for (int qx = 0; qx < Q; qx++) s += dm.M[sel][qx * P + i] * Aq[d][qx];
+            R0[IDX(d, i, a, b)] = s;
+          }
+        }
+      }
+      __syncthreads();
+      // y-lines (a = i < P, b = qz)
+      if (act && a < P) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const int sel = (d == 1) + (dp == 1);
+          double in[Q];
+#pragma unroll
+          for (int qy = 0; qy < Q; qy++) in[qy] = R0[IDX(d, a, qy, b)];
+#pragma unroll
+          for (int j = 0; j < P; j++) {
+            double s = 0;
+#pragma unroll
+            for (int qy = 0; qy < Q; qy++) s += dm.M[sel][qy * P + j] * in[qy];
+            R1[IDX(d, a, j, b)] = s;
+          }
+        }
+      }
+      __syncthreads();
+      // z-lines (a = i < P, b = j < P)
+      if (act && a < P && b < P) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const int sel = (d == 2) + (dp == 2);
+          double in[Q];
+#pragma unroll
+          for (int qz = 0; qz < Q; qz++) in[qz] = R1[IDX(d, a, b, qz)];
+#pragma unroll
+          for (int k = 0; k < P; k++) {
+            double s = 0;
+#pragma unroll
+            for (int qz = 0; qz < Q; qz++) s += dm.M[sel][qz * P + k] * in[qz];
+            acc[k] += s;
+          }
+        }
+      }
+      // R0 is rewritten only after the next iteration's first barrier-protected stage has
+      // been preceded by this iteration's second barrier; R1 readers (z-lines) must finish
+      // before the next y-line stage writes R1: that stage sits behind the next barrier.
+    }
+    if (act && a < P && b < P) {
+#pragma unroll
+      for (int k = 0; k < P; k++) {
+        const int o = __ldg(offsets + (size_t)e * P3 + (k * P + b) * P + a);
+        atomicAdd(diag + o + c, acc[k]);
+      }
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------
+// p-multigrid transfer: out_L += Eo^T I^(T) Ei in_L  (matops.c:115-203)
+// PC nodes -> PF nodes with the interpolation matrix J [PF][PC]; same line machinery.
+// -----------------------------------------------------------------------------------
+template <int PC, int PF> struct XferMats { double J[PF * PC]; };
+
+template <int PC, int PF, int TR>
+__global__ void __launch_bounds__(Cfg<PF>::NT)
+k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__restrict__ offc,
+           const int *__restrict__ offf, const double *__restrict__ mult, const double *__restrict__ in,
+           double *__restrict__ out) {
+  constexpr int Q = PF;  // lattice extent used for smem indexing
+  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE;
+  constexpr int NI = TR ? PF : PC, NO = TR ? PC : PF;  // line extents in / out
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int eb = tid / T, t = tid - eb * T, a = t % Q, b = t / Q;
+  const int rem = nelem - blockIdx.x * EB;
+  const int ebn = rem < EB ? rem : EB;
+  const bool act = eb < ebn;
+  const int e = blockIdx.x * EB + eb;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * Q3;
+  const int *oin = (TR ? offf : offc) + (size_t)e * NI * NI * NI;
+  const int *oout = (TR ? offc : offf) + (size_t)e * NO * NO * NO;
+#define JM(o, i) (TR ? m.J[(i) * PC + (o)] : m.J[(o) * PC + (i)])
+  // z-lines (a = i, b = j) gather + contract z
+  if (act && a < NI && b < NI) {
+    double r[3][NI];
+#pragma unroll
+    for (int k = 0; k < NI; k++) {
+      const int o = __ldg(oin + (k * NI + b) * NI + a);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        double v = __ldg(in + o + c);
+        if (TR && mult) v *= __ldg(mult + o + c);
+        r[c][k] = v;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int z = 0; z < NO; z++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NI; k++) s += JM(z, k) * r[c][k];
+        R0[IDX(c, a, b, z)] = s;
+      }
+  }
+  __syncthreads();
+  // y-lines (a = i < NI, b = z < NO)
+  if (act && a < NI && b < NO) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double l[NI];
+#pragma unroll
+      for (int j = 0; j < NI; j++) l[j] = R0[IDX(c, a, j, b)];
+#pragma unroll
+      for (int yy = 0; yy < NO; yy++) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < NI; j++) s += JM(yy, j) * l[j];
+        R1[IDX(c, a, yy, b)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // x-lines (a = y < NO, b = z < NO), scatter
+  if (act && a < NO && b < NO) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double l[NI];
+#pragma unroll
+      for (int i = 0; i < NI; i++) l[i] = R1[IDX(c, i, a, b)];
+#pragma unroll
+      for (int xx = 0; xx < NO; xx++) {
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < NI; i++) s += JM(xx, i) * l[i];
+        const int o = __ldg(oout + (b * NO + a) * NO + xx);
+        if (!TR && mult) s *= __ldg(mult + o + c);
+        atomicAdd(out + o + c, s);
+      }
+    }
+  }
+#undef JM
+}
+
+// -----------------------------------------------------------------------------------
+// host side
+// -----------------------------------------------------------------------------------
+
+// Gc = D * pinv(B): the unique-on-range(B) matrix with Gc B = D (P <= Q, B full column rank).
+static int collocated_grad(int P, int Q, const double *B, const double *D, double *Gc) {
+  double N[8 * 8], Ninv[8 * 8], tmp[8 * 8];
+  for (int i = 0; i < P; i++)
+    for (int j = 0; j < P; j++) {
+      double s = 0;
+      for (int q = 0; q < Q; q++) s += B[q * P + i] * B[q * P + j];
+      N[i * P + j] = s;
+      Ninv[i * P + j] = i == j ? 1.0 : 0.0;
+    }
+  for (int col = 0; col < P; col++) {  // Gauss-Jordan with partial pivoting
+    int piv = col;
+    for (int r = col + 1; r < P; r++)
+      if (fabs(N[r * P + col]) > fabs(N[piv * P + col])) piv = r;
+    if (fabs(N[piv * P + col]) < 1e-300) return 1;
+    if (piv != col)
+      for (int j = 0; j < P; j++) {
+        double t = N[col * P + j]; N[col * P + j] = N[piv * P + j]; N[piv * P + j] = t;
+        t = Ninv[col * P + j]; Ninv[col * P + j] = Ninv[piv * P + j]; Ninv[piv * P + j] = t;
+      }
+    const double d = 1.0 / N[col * P + col];
+    for (int j = 0; j < P; j++) { N[col * P + j] *= d; Ninv[col * P + j] *= d; }
+    for (int r = 0; r < P; r++)
+      if (r != col) {
+        const double f = N[r * P + col];
+        for (int j = 0; j < P; j++) { N[r * P + j] -= f * N[col * P + j]; Ninv[r * P + j] -= f * Ninv[col * P + j]; }
+      }
+  }
+  // tmp = D * Ninv  [Q][P];  Gc = tmp * B^T  [Q][Q]
+  for (int q = 0; q < Q; q++)
+    for (int j = 0; j < P; j++) {
+      double s = 0;
+      for (int i = 0; i < P; i++) s += D[q * P + i] * Ninv[i * P + j];
+      tmp[q * P + j] = s;
+    }
+  for (int q = 0; q < Q; q++)
+    for (int r = 0; r < Q; r++) {
+      double s = 0;
+      for (int j = 0; j < P; j++) s += tmp[q * P + j] * B[r * P + j];
+      Gc[q * Q + r] = s;
+    }
+  // one step of iterative refinement is unnecessary at these sizes; verify instead
+  double err = 0, nrm = 0;
+  for (int q = 0; q < Q; q++)
+    for (int i = 0; i < P; i++) {
+      double s = 0;
+      for (int r = 0; r < Q; r++) s += Gc[q * Q + r] * B[r * P + i];
+      err = fmax(err, fabs(s - D[q * P + i]));
+      nrm = fmax(nrm, fabs(D[q * P + i]));
+    }
+  return err <= 1e-12 * nrm ? 0 : 2;
+}
+
+template <typename K> static int opt_in_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) B200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int P, int Q, int PROB, int MODE>
+static int launch_apply(const Material &mt, int nelem, const double *hB, const double *hD, const int *offsets,
+                        const double *qa, double *gradu, const double *x, double *y) {
+  Mats<P, Q> m;
+  for (int i = 0; i < Q * P; i++) m.B[i] = hB[i];
+  if (collocated_grad(P, Q, hB, hD, m.Gc)) return set_error_msg("basis: no collocated gradient with Gc*B = D (rank-deficient interp1d)");
+  auto kern = k_fused_apply<P, Q, PROB, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = opt_in_smem(kern, Cfg<Q>::SMEM)) return rc;
+    configured = true;
+  }
+  const int nblk = (nelem + Cfg<Q>::EB - 1) / Cfg<Q>::EB;
+  if (nblk == 0) return 0;
+  kern<<<nblk, Cfg<Q>::NT, Cfg<Q>::SMEM, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y);
+  B200_LAUNCH_CHECK("k_fused_apply");
+  return 0;
+}
+
+template <int P, int Q, int PROB>
+static int launch_diag(const Material &mt, int nelem, const double *hB, const double *hD, const int *offsets,
+                       const double *jc, double *diag) {
+  DiagMats<P, Q> dm;
+  for (int i = 0; i < Q * P; i++) {
+    dm.M[0][i] = hB[i] * hB[i];
+    dm.M[1][i] = hB[i] * hD[i];
+    dm.M[2][i] = hD[i] * hD[i];
+  }
+  auto kern = k_fused_diag<P, Q, PROB>;
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = opt_in_smem(kern, Cfg<Q>::SMEM)) return rc;
+    configured = true;
+  }
+  const int nblk = (nelem + Cfg<Q>::EB - 1) / Cfg<Q>::EB;
+  if (nblk == 0) return 0;
+  kern<<<nblk, Cfg<Q>::NT, Cfg<Q>::SMEM, g_stream>>>(dm, mt, nelem, offsets, jc, diag);
+  B200_LAUNCH_CHECK("k_fused_diag");
+  return 0;
+}
+
+template <int PC, int PF, int TR>
+static int launch_transfer(int nelem, const double *hJ, const int *offc, const int *offf, const double *mult,
+                           const double *in, double *out) {
+  XferMats<PC, PF> m;
+  for (int i = 0; i < PF * PC; i++) m.J[i] = hJ[i];
+  auto kern = k_transfer<PC, PF, TR>;
+  static bool configured = false;
+  if (!configured) {
+    if (int rc = opt_in_smem(kern, Cfg<PF>::SMEM)) return rc;
+    configured = true;
+  }
+  const int nblk = (nelem + Cfg<PF>::EB - 1) / Cfg<PF>::EB;
+  if (nblk == 0) return 0;
+  kern<<<nblk, Cfg<PF>::NT, Cfg<PF>::SMEM, g_stream>>>(m, nelem, offc, offf, mult, in, out);
+  B200_LAUNCH_CHECK("k_transfer");
+  return 0;
+}
+
+// (P, Q) pairs instantiated: every level of p-MG hierarchies up to degree 4 with qextra 0/1
+#define B200_FOR_PQ(X) \
+  X(2, 2) X(2, 3) X(3, 3) X(2, 4) X(3, 4) X(4, 4) X(2, 5) X(3, 5) X(4, 5) X(5, 5) X(2, 6) X(3, 6) X(5, 6)
+
+template <int PROB, int MODE>
+static int dispatch_apply(int P, int Q, const Material &mt, int nelem, const double *hB, const double *hD,
+                          const int *offsets, const double *qa, double *gradu, const double *x, double *y) {
+#define X(p, q) \
+  if (P == p && Q == q) return launch_apply<p, q, PROB, MODE>(mt, nelem, hB, hD, offsets, qa, gradu, x, y);
+  B200_FOR_PQ(X)
+#undef X
+  return set_error_msg("fused apply: (P,Q) not instantiated");
+}
+
+template <int PROB>
+static int dispatch_diag(int P, int Q, const Material &mt, int nelem, const double *hB, const double *hD,
+                         const int *offsets, const double *jc, double *diag) {
+#define X(p, q) \
+  if (P == p && Q == q) return launch_diag<p, q, PROB>(mt, nelem, hB, hD, offsets, jc, diag);
+  B200_FOR_PQ(X)
+#undef X
+  return set_error_msg("fused diagonal: (P,Q) not instantiated");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_fused_supported(int P, int Q) {
+#define X(p, q) \
+  if (P == p && Q == q) return 1;
+  B200_FOR_PQ(X)
+#undef X
+  return 0;
+}
+
+extern "C" int b200_jcache_ncomp(int problem) {
+  return problem == B200_PROB_LINELAS ? 10 : problem == B200_PROB_HYPERSS ? 11 : problem == B200_PROB_HYPERFS ? 17 : -1;
+}
+
+extern "C" int b200_apply_residual(int problem, const b200_physics *phys, int nelem, int P, int Q,
+                                   const double *hB, const double *hD, const int *d_offsets,
+                                   const double *d_qdata, double *d_gradu, const double *d_x, double *d_y) {
+  const Material mt = make_material(phys);
+  switch (problem) {
+    case B200_PROB_LINELAS: return dispatch_apply<B200_PROB_LINELAS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y);
+    case B200_PROB_HYPERSS: return dispatch_apply<B200_PROB_HYPERSS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y);
+    case B200_PROB_HYPERFS: return dispatch_apply<B200_PROB_HYPERFS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y);
+  }
+  return set_error_msg("b200_apply_residual: unknown problem");
+}
+
+extern "C" int b200_apply_jacobian(int problem, const b200_physics *phys, int nelem, int P, int Q,
+                                   const double *hB, const double *hD, const int *d_offsets,
+                                   const double *d_jcache, const double *d_x, double *d_y) {
+  const Material mt = make_material(phys);
+  switch (problem) {
+    case B200_PROB_LINELAS: return dispatch_apply<B200_PROB_LINELAS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y);
+    case B200_PROB_HYPERSS: return dispatch_apply<B200_PROB_HYPERSS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y);
+    case B200_PROB_HYPERFS: return dispatch_apply<B200_PROB_HYPERFS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y);
+  }
+  return set_error_msg("b200_apply_jacobian: unknown problem");
+}
+
+extern "C" int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P, int Q,
+                                   const double *hB, const double *hD, const int *d_offsets,
+                                   const double *d_jcache, double *d_diag) {
+  const Material mt = make_material(phys);
+  switch (problem) {
+    case B200_PROB_LINELAS: return dispatch_diag<B200_PROB_LINELAS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag);
+    case B200_PROB_HYPERSS: return dispatch_diag<B200_PROB_HYPERSS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag);
+    case B200_PROB_HYPERFS: return dispatch_diag<B200_PROB_HYPERFS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag);
+  }
+  return set_error_msg("b200_apply_diagonal: unknown problem");
+}
+
+extern "C" int b200_jcache_build(int problem, int nelem, int Q, const double *d_qdata, const double *d_gradu,
+                                 double *d_jcache) {
+  if (Q < 2 || Q > 8) return set_error_msg("b200_jcache_build: Q out of range");
+  if (nelem == 0) return 0;
+  const size_t npts = (size_t)nelem * Q * Q * Q;
+  const int nt = 256;
+  size_t nb = (npts + nt - 1) / nt;
+  if (nb > 148 * 64) nb = 148 * 64;
+  switch (problem) {
+    case B200_PROB_LINELAS: k_jcache_build<B200_PROB_LINELAS><<<(int)nb, nt, 0, g_stream>>>(nelem, Q, d_qdata, d_gradu, d_jcache); break;
+    case B200_PROB_HYPERSS: k_jcache_build<B200_PROB_HYPERSS><<<(int)nb, nt, 0, g_stream>>>(nelem, Q, d_qdata, d_gradu, d_jcache); break;
+    case B200_PROB_HYPERFS: k_jcache_build<B200_PROB_HYPERFS><<<(int)nb, nt, 0, g_stream>>>(nelem, Q, d_qdata, d_gradu, d_jcache); break;
+    default: return set_error_msg("b200_jcache_build: unknown problem");
+  }
+  B200_LAUNCH_CHECK("k_jcache_build");
+  return 0;
+}
+
+extern "C" int b200_apply_transfer(int transpose, int nelem, int Pc, int Pf, const double *hJ, const int *d_offc,
+                                   const int *d_offf, const double *d_mult, const double *d_in, double *d_out) {
+#define XF(pc, pf)                                                                                      \
+  if (Pc == pc && Pf == pf)                                                                             \
+    return transpose ? launch_transfer<pc, pf, 1>(nelem, hJ, d_offc, d_offf, d_mult, d_in, d_out)       \
+                     : launch_transfer<pc, pf, 0>(nelem, hJ, d_offc, d_offf, d_mult, d_in, d_out);
+  XF(2, 3) XF(3, 4) XF(4, 5) XF(3, 5) XF(2, 4) XF(2, 5)
+#undef XF
+  return set_error_msg("b200_apply_transfer: (Pc,Pf) not instantiated");
+}

@@ -1,0 +1,240 @@
+// Generic (non-fused) operator path of the /gpu/b200 backend: stand-alone
+// CeedElemRestrictionApply, CeedBasisApply and CeedQFunctionApply kernels
+// (SURVEY.md App. B.1-B.4).  Used for every operator the fused kernels do not cover:
+// the geometric-factor set-up (setuplibceed.c:370-393), identity-QFunction transfers,
+// restriction multiplicity (misc.c:117-123), ... -- all on the GPU, no host fallback.
+// These run once per set-up, not per Krylov iteration; they are written for clarity.
+#include "b200_qf.cuh"
+
+namespace b200 {
+
+#define GRID_STRIDE(i, n) \
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+
+static inline int grid_for(size_t n, int nt) {
+  size_t nb = (n + nt - 1) / nt;
+  const size_t cap = 148 * 32;
+  return (int)(nb > cap ? cap : (nb ? nb : 1));
+}
+
+// ---- B.1 restrictions --------------------------------------------------------------
+__global__ void k_restrict_offsets(int transpose, size_t total, int elemsize, int ncomp, int compstride,
+                                   const int *__restrict__ offsets, const double *__restrict__ in,
+                                   double *__restrict__ out) {
+  GRID_STRIDE(i, total) {  // i = (e*ncomp + c)*elemsize + n
+    const size_t n = i % elemsize, ec = i / elemsize;
+    const size_t c = ec % ncomp, e = ec / ncomp;
+    const size_t l = (size_t)offsets[e * elemsize + n] + c * (size_t)compstride;
+    if (!transpose) out[i] = in[l];
+    else atomicAdd(out + l, in[i]);
+  }
+}
+
+__global__ void k_restrict_strided(int transpose, size_t total, int nelem, int elemsize, int ncomp, int layout_q,
+                                   long long s_node, long long s_comp, long long s_elem,
+                                   const double *__restrict__ in, double *__restrict__ out) {
+  GRID_STRIDE(i, total) {
+    const int n = (int)(i % elemsize);
+    const size_t ec = i / elemsize;
+    const int c = (int)(ec % ncomp), e = (int)(ec / ncomp);
+    const size_t l = layout_q ? qblocked_index(nelem, ncomp, layout_q, e, c, n)
+                              : (size_t)(n * s_node + c * s_comp + e * s_elem);
+    if (!transpose) out[i] = in[l];
+    else out[l] += in[i];  // strided restrictions are one-to-one: no atomics needed
+  }
+}
+
+// ---- B.3 tensor basis --------------------------------------------------------------
+// One CTA per element.  Three 1-D contractions, x (fastest index) first; buffers in smem.
+// out[a][j][c] = sum_b M(j,b) in[a][b][c];  M is [Q][P] used plain (J=Q,B=P) or transposed.
+__device__ void stage(const double *in, double *out, const double *M, int tr, int P, int A, int Bd, int C, int J,
+                      bool add) {
+  const int total = A * J * C;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int c = idx % C, j = (idx / C) % J, a = idx / (C * J);
+    double s = 0;
+    for (int b = 0; b < Bd; b++) s += (tr ? M[b * P + j] : M[j * P + b]) * in[(a * Bd + b) * C + c];
+    if (add) out[idx] += s;
+    else out[idx] = s;
+  }
+}
+
+__global__ void k_basis_apply(int ncomp, int P, int Q, const double *__restrict__ interp1d,
+                              const double *__restrict__ grad1d, const double *__restrict__ qweight1d, int tr,
+                              int emode, const double *__restrict__ u, double *__restrict__ v) {
+  extern __shared__ double sm[];
+  const int P3 = P * P * P, Q3 = Q * Q * Q, mx = P > Q ? P : Q;
+  const int e = blockIdx.x;
+  double *sB = sm, *sD = sB + Q * P, *b0 = sD + Q * P, *b1 = b0 + ncomp * mx * mx * mx, *b2 = b1 + ncomp * mx * mx * mx;
+  for (int i = threadIdx.x; i < Q * P; i += blockDim.x) { sB[i] = interp1d[i]; sD[i] = grad1d[i]; }
+  if (emode == 4) {
+    for (int q = threadIdx.x; q < Q3; q += blockDim.x)
+      v[(size_t)e * Q3 + q] = qweight1d[q % Q] * qweight1d[(q / Q) % Q] * qweight1d[q / (Q * Q)];
+    return;
+  }
+  const int nin = tr ? Q : P, nout = tr ? P : Q;
+  const int in3 = nin * nin * nin, out3 = nout * nout * nout;
+  const int ndir = emode == 2 ? 3 : 1;
+  const size_t usz = tr ? (size_t)ndir * ncomp * Q3 : (size_t)ncomp * P3;
+  const size_t vsz = tr ? (size_t)ncomp * P3 : (size_t)ndir * ncomp * Q3;
+  __syncthreads();
+  for (int d = 0; d < ndir; d++) {
+    const double *m0 = (emode == 2 && d == 0) ? sD : sB;
+    const double *m1 = (emode == 2 && d == 1) ? sD : sB;
+    const double *m2 = (emode == 2 && d == 2) ? sD : sB;
+    const double *src = u + (size_t)e * usz + (tr ? (size_t)d * ncomp * Q3 : 0);
+    for (int i = threadIdx.x; i < ncomp * in3; i += blockDim.x) b0[i] = src[i];
+    __syncthreads();
+    stage(b0, b1, m0, tr, P, ncomp * nin * nin, nin, 1, nout, false);
+    __syncthreads();
+    stage(b1, b0, m1, tr, P, ncomp * nin, nin, nout, nout, false);
+    __syncthreads();
+    if (!tr) {
+      stage(b0, b1, m2, tr, P, ncomp, nin, nout * nout, nout, false);
+      __syncthreads();
+      double *dst = v + (size_t)e * vsz + (size_t)d * ncomp * Q3;
+      for (int i = threadIdx.x; i < ncomp * out3; i += blockDim.x) dst[i] = b1[i];
+    } else {
+      stage(b0, b2, m2, tr, P, ncomp, nin, nout * nout, nout, d > 0);
+    }
+    __syncthreads();
+  }
+  if (tr) {
+    double *dst = v + (size_t)e * vsz;
+    for (int i = threadIdx.x; i < ncomp * out3; i += blockDim.x) dst[i] = b2[i];
+  }
+}
+
+// ---- B.4 QFunctions ------------------------------------------------------------------
+struct QFArgs {
+  const double *in[4];
+  double *out[4];
+};
+
+// Q-vectors are [elem][size][nq]; thread per (elem, q)
+__global__ void k_qfunction(int qf, const __grid_constant__ Material mt, int isize, int nelem, int nq,
+                            const __grid_constant__ QFArgs a) {
+  const size_t total = (size_t)nelem * nq;
+  GRID_STRIDE(i, total) {
+    const size_t e = i / nq, q = i % nq;
+#define IN(k, sz, comp) a.in[k][(e * (sz) + (comp)) * nq + q]
+#define OUT(k, sz, comp) a.out[k][(e * (sz) + (comp)) * nq + q]
+    if (qf == B200_QF_IDENTITY) {
+      for (int c = 0; c < isize; c++) OUT(0, isize, c) = IN(0, isize, c);
+      continue;
+    }
+    if (qf == B200_QF_SETUPGEO) {  // qfunctions/common.h:47-101
+      double J[3][3];            // J[c][d] = dx_c/dX_d = in0[d][c]
+      for (int d = 0; d < 3; d++)
+        for (int c = 0; c < 3; c++) J[c][d] = IN(0, 9, d * 3 + c);
+      double Ad[3][3];
+      Ad[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+      Ad[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+      Ad[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+      Ad[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      Ad[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+      Ad[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+      Ad[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      Ad[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+      Ad[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      const double detJ = J[0][0] * Ad[0][0] + J[1][0] * Ad[0][1] + J[2][0] * Ad[0][2];
+      OUT(0, 10, 0) = IN(1, 1, 0) * detJ;
+      for (int r = 0; r < 3; r++)
+        for (int s = 0; s < 3; s++) OUT(0, 10, 1 + 3 * r + s) = Ad[r][s] / detJ;
+      continue;
+    }
+    // solid-mechanics point functions: in0 = du [d][c], in1 = qdata[10], (in2 = gradu [c][k])
+    double H[3][3], A[3][3], W[3][3], g[3][3];
+    for (int d = 0; d < 3; d++)
+      for (int c = 0; c < 3; c++) H[c][d] = IN(0, 9, d * 3 + c);
+    const double w = IN(1, 10, 0);
+    for (int r = 0; r < 3; r++)
+      for (int s = 0; s < 3; s++) A[r][s] = IN(1, 10, 1 + 3 * r + s);
+    bool store_g = false;
+    switch (qf) {
+      case B200_QF_LINELAS_F:
+      case B200_QF_LINELAS_DF: linelas_point(mt, w, A, H, W); break;
+      case B200_QF_HYPERSS_F: hyperss_f_point(mt, w, A, H, g, W); store_g = true; break;
+      case B200_QF_HYPERFS_F: hyperfs_f_point(mt, w, A, H, g, W); store_g = true; break;
+      case B200_QF_HYPERSS_DF: {
+        const double s = 1. / (1. + (IN(2, 9, 0) + IN(2, 9, 4) + IN(2, 9, 8)));
+        hyperss_df_point(mt, w, A, s, H, W);
+      } break;
+      case B200_QF_HYPERFS_DF: {
+        for (int c = 0; c < 3; c++)
+          for (int k = 0; k < 3; k++) g[c][k] = IN(2, 9, c * 3 + k);
+        hyperfs_df_point_faithful(mt, w, A, g, H, W);
+      } break;
+      default: return;
+    }
+    for (int k = 0; k < 3; k++)
+      for (int c = 0; c < 3; c++) OUT(0, 9, k * 3 + c) = W[c][k];
+    if (store_g)
+      for (int c = 0; c < 3; c++)
+        for (int k = 0; k < 3; k++) OUT(1, 9, c * 3 + k) = g[c][k];
+#undef IN
+#undef OUT
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_restrict_offsets(int transpose, int nelem, int elemsize, int ncomp, int compstride,
+                                     const int *d_offsets, const double *d_in, double *d_out) {
+  const size_t total = (size_t)nelem * ncomp * elemsize;
+  if (!total) return 0;
+  k_restrict_offsets<<<grid_for(total, 256), 256, 0, g_stream>>>(transpose, total, elemsize, ncomp, compstride,
+                                                                 d_offsets, d_in, d_out);
+  B200_LAUNCH_CHECK("k_restrict_offsets");
+  return 0;
+}
+
+extern "C" int b200_restrict_strided(int transpose, int nelem, int elemsize, int ncomp, int layout_q,
+                                     long long s_node, long long s_comp, long long s_elem, const double *d_in,
+                                     double *d_out) {
+  const size_t total = (size_t)nelem * ncomp * elemsize;
+  if (!total) return 0;
+  k_restrict_strided<<<grid_for(total, 256), 256, 0, g_stream>>>(transpose, total, nelem, elemsize, ncomp, layout_q,
+                                                                 s_node, s_comp, s_elem, d_in, d_out);
+  B200_LAUNCH_CHECK("k_restrict_strided");
+  return 0;
+}
+
+extern "C" int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double *d_interp1d, const double *d_grad1d,
+                                const double *d_qweight1d, int transpose, int emode, const double *d_u, double *d_v) {
+  if (!nelem) return 0;
+  if (P > 10 || Q > 10) return set_error_msg("b200_basis_apply: P, Q <= 10 supported");
+  if (emode != 1 && emode != 2 && emode != 4) return set_error_msg("b200_basis_apply: eval mode not supported");
+  const int mx = P > Q ? P : Q;
+  const size_t smem = sizeof(double) * (2 * (size_t)Q * P + 3 * (size_t)ncomp * mx * mx * mx);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    B200_CHECK(cudaFuncSetAttribute(k_basis_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_basis_apply<<<nelem, 128, smem, g_stream>>>(ncomp, P, Q, d_interp1d, d_grad1d, d_qweight1d, transpose, emode, d_u, d_v);
+  B200_LAUNCH_CHECK("k_basis_apply");
+  return 0;
+}
+
+extern "C" int b200_qfunction_apply(int qf_id, const b200_physics *phys, int identity_size, int nelem, int nq, int nin,
+                                    const double *const *d_in, int nout, double *const *d_out) {
+  if (nin > 4 || nout > 4) return set_error_msg("b200_qfunction_apply: at most 4 input and 4 output fields");
+  const int need_in = qf_id == B200_QF_IDENTITY ? 1 : (qf_id == B200_QF_HYPERSS_DF || qf_id == B200_QF_HYPERFS_DF) ? 3 : 2;
+  const int need_out = (qf_id == B200_QF_HYPERSS_F || qf_id == B200_QF_HYPERFS_F) ? 2 : 1;
+  if (qf_id <= B200_QF_NONE || qf_id > B200_QF_IDENTITY) return set_error_msg("b200_qfunction_apply: unknown QFunction id");
+  if (nin < need_in || nout < need_out) return set_error_msg("b200_qfunction_apply: field count does not match the QFunction");
+  QFArgs a;
+  memset(&a, 0, sizeof a);
+  for (int i = 0; i < nin; i++) a.in[i] = d_in[i];
+  for (int i = 0; i < nout; i++) a.out[i] = d_out[i];
+  b200_physics dflt = {0.3, 1.0};
+  const Material mt = make_material(phys ? phys : &dflt);
+  const size_t total = (size_t)nelem * nq;
+  if (!total) return 0;
+  k_qfunction<<<grid_for(total, 128), 128, 0, g_stream>>>(qf_id, mt, identity_size, nelem, nq, a);
+  B200_LAUNCH_CHECK("k_qfunction");
+  return 0;
+}

@@ -1,0 +1,320 @@
+// Device bodies of the recognised QFunctions (hand-written; the user headers
+// /root/reference/qfunctions/*.h stay untouched and are what the oracle runs).
+//
+// Conventions:
+//   H[c][m] = d u_c / d X_m          reference-space gradient of component c   (QFunction in0[m][c])
+//   A[m][k] = dXdx[m][k]             qdata[1 + 3m + k]
+//   g[c][k] = sum_m A[m][k] H[c][m]  physical gradient
+//   W[c][k]                          QFunction out0[k][c] = w * sum_m A[k][m] T[c][m]
+#pragma once
+#include "b200_common.cuh"
+
+namespace b200 {
+
+#define B200_DI __device__ __forceinline__
+
+B200_DI void phys_grad(const double (&A)[3][3], const double (&H)[3][3], double (&g)[3][3]) {
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) g[c][k] = A[0][k] * H[c][0] + A[1][k] * H[c][1] + A[2][k] * H[c][2];
+}
+
+// W[c][k] = sum_m A[k][m] * T[c][m]   (T already scaled by w*detJ)
+B200_DI void pull_back(const double (&A)[3][3], const double (&T)[3][3], double (&W)[3][3]) {
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) W[c][k] = A[k][0] * T[c][0] + A[k][1] * T[c][1] + A[k][2] * T[c][2];
+}
+
+// ------------------------------------------------------------------ linear elasticity
+// qfunctions/linElas.h:97-153 (F) == :221-275 (dF).  The shear entries keep the
+// reference's extra factor 0.5 (linElas.h:137-139).
+B200_DI void linelas_point(const Material &mt, double w, const double (&A)[3][3],
+                           const double (&H)[3][3], double (&W)[3][3]) {
+  double g[3][3], T[3][3];
+  phys_grad(A, H, g);
+  const double c1 = mt.le_c1 * w, c2 = mt.le_c2 * w, c3 = mt.le_c3 * w;
+  T[0][0] = c1 * g[0][0] + c2 * (g[1][1] + g[2][2]);
+  T[1][1] = c1 * g[1][1] + c2 * (g[0][0] + g[2][2]);
+  T[2][2] = c1 * g[2][2] + c2 * (g[0][0] + g[1][1]);
+  T[0][1] = T[1][0] = c3 * (g[0][1] + g[1][0]);
+  T[0][2] = T[2][0] = c3 * (g[0][2] + g[2][0]);
+  T[1][2] = T[2][1] = c3 * (g[1][2] + g[2][1]);
+  pull_back(A, T, W);
+}
+
+// ------------------------------------------------------------------ hyperSS
+// qfunctions/hyperSS.h:43-55
+B200_DI double log1p_series(double x) {
+  double y = x / (2. + x);
+  const double y2 = y * y;
+  double sum = y;
+  y *= y2; sum += y / 3;
+  y *= y2; sum += y / 5;
+  y *= y2; sum += y / 7;
+  return 2 * sum;
+}
+
+// residual, qfunctions/hyperSS.h:112-177; g (= gradu to store) is returned
+B200_DI void hyperss_f_point(const Material &mt, double w, const double (&A)[3][3],
+                             const double (&H)[3][3], double (&g)[3][3], double (&W)[3][3]) {
+  double T[3][3];
+  phys_grad(A, H, g);
+  const double llv = mt.lambda * log1p_series(g[0][0] + g[1][1] + g[2][2]) * w;
+  const double mw = mt.mu * w;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) T[a][b] = mw * (g[a][b] + g[b][a]) + (a == b ? llv : 0.);
+  pull_back(A, T, W);
+}
+
+// Jacobian, qfunctions/hyperSS.h:239-316; s = 1 / (1 + tr gradu)
+B200_DI void hyperss_df_point(const Material &mt, double w, const double (&A)[3][3], double s,
+                              const double (&H)[3][3], double (&W)[3][3]) {
+  double g[3][3], T[3][3];
+  phys_grad(A, H, g);
+  const double ltr = (mt.lambda * s * w) * (g[0][0] + g[1][1] + g[2][2]);
+  const double mw = mt.mu * w;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) T[a][b] = mw * (g[a][b] + g[b][a]) + (a == b ? ltr : 0.);
+  pull_back(A, T, W);
+}
+
+// ------------------------------------------------------------------ hyperFS
+// qfunctions/hyperFS.h:45-67
+B200_DI double log1p_series_shifted(double x) {
+  const double left = 0.70710678118654752440 - 1, right = 1.41421356237309504880 - 1;
+  const double half_ln2 = 0.34657359027997265471;
+  double sum = 0;
+  if (x < left) {
+    sum -= half_ln2;
+    x = 1 + 2 * x;
+  } else if (right < x) {
+    sum += half_ln2;
+    x = (x - 1) / 2;
+  }
+  double y = x / (2. + x);
+  const double y2 = y * y;
+  sum += y;
+  y *= y2; sum += y / 3;
+  y *= y2; sum += y / 5;
+  y *= y2; sum += y / 7;
+  return 2 * sum;
+}
+
+// 2E in Voigt order (00,11,22,12,02,01) and det(C) - 1 (hyperFS.h:72-80, :91-97)
+B200_DI double green_lagrange2(const double (&g)[3][3], double (&e)[6]) {
+  const int vj[6] = {0, 1, 2, 1, 0, 0}, vk[6] = {0, 1, 2, 2, 2, 1};
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+    const int j = vj[m], k = vk[m];
+    e[m] = g[j][k] + g[k][j] + g[0][j] * g[0][k] + g[1][j] * g[1][k] + g[2][j] * g[2][k];
+  }
+  return e[0] * (e[1] * e[2] - e[3] * e[3]) + e[5] * (e[4] * e[3] - e[5] * e[2]) +
+         e[4] * (e[5] * e[3] - e[4] * e[1]) + e[0] + e[1] + e[2] + e[0] * e[1] + e[0] * e[2] +
+         e[1] * e[2] - e[5] * e[5] - e[4] * e[4] - e[3] * e[3];
+}
+
+B200_DI void voigt_sym(const double (&v)[6], double (&m)[3][3]) {
+  m[0][0] = v[0]; m[1][1] = v[1]; m[2][2] = v[2];
+  m[1][2] = m[2][1] = v[3];
+  m[0][2] = m[2][0] = v[4];
+  m[0][1] = m[1][0] = v[5];
+}
+
+// commonFS, hyperFS.h:85-142: S, C^-1 (full symmetric) and llnj = lambda log J
+B200_DI void fs_common(const Material &mt, const double (&g)[3][3], double (&S)[3][3],
+                       double (&Ci)[3][3], double &llnj) {
+  double e[6], E2[3][3], C[3][3], civ[6], sv[6];
+  const double detC_m1 = green_lagrange2(g, e);
+  voigt_sym(e, E2);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) C[a][b] = E2[a][b] + (a == b ? 1. : 0.);
+  const double Adj[6] = {C[1][1] * C[2][2] - C[1][2] * C[2][1], C[0][0] * C[2][2] - C[0][2] * C[2][0],
+                         C[0][0] * C[1][1] - C[0][1] * C[1][0], C[0][2] * C[1][0] - C[0][0] * C[1][2],
+                         C[0][1] * C[1][2] - C[0][2] * C[1][1], C[0][2] * C[2][1] - C[0][1] * C[2][2]};
+  const double rdet = 1. / (detC_m1 + 1.);
+#pragma unroll
+  for (int m = 0; m < 6; m++) civ[m] = Adj[m] * rdet;
+  voigt_sym(civ, Ci);
+  llnj = mt.lambda * log1p_series_shifted(detC_m1) / 2.;
+  const int vj[6] = {0, 1, 2, 1, 0, 0}, vk[6] = {0, 1, 2, 2, 2, 1};
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+    double s = llnj * civ[m];
+#pragma unroll
+    for (int n = 0; n < 3; n++) s += mt.mu * Ci[vj[m]][n] * E2[n][vk[m]];
+    sv[m] = s;
+  }
+  voigt_sym(sv, S);
+}
+
+// residual, hyperFS.h:212-276
+B200_DI void hyperfs_f_point(const Material &mt, double w, const double (&A)[3][3],
+                             const double (&H)[3][3], double (&g)[3][3], double (&W)[3][3]) {
+  double S[3][3], Ci[3][3], llnj, F[3][3], Pk[3][3];
+  phys_grad(A, H, g);
+  fs_common(mt, g, S, Ci, llnj);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) F[a][b] = g[a][b] + (a == b ? 1. : 0.);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) Pk[a][b] = (F[a][0] * S[0][b] + F[a][1] * S[1][b] + F[a][2] * S[2][b]) * w;
+  pull_back(A, Pk, W);
+}
+
+// Jacobian in the reference's own algebra (hyperFS.h:339-459), used by the generic
+// (non-fused) operator path and to cross-check the cached form on the device.
+B200_DI void hyperfs_df_point_faithful(const Material &mt, double w, const double (&A)[3][3],
+                                       const double (&g)[3][3], const double (&H)[3][3],
+                                       double (&W)[3][3]) {
+  double S[3][3], Ci[3][3], llnj, F[3][3], gd[3][3], dE[3][3], dECi[3][3], dS[3][3], dP[3][3];
+  phys_grad(A, H, gd);
+  fs_common(mt, g, S, Ci, llnj);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) F[a][b] = g[a][b] + (a == b ? 1. : 0.);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      double s = 0;
+#pragma unroll
+      for (int n = 0; n < 3; n++) s += (gd[n][a] * F[n][b] + F[n][a] * gd[n][b]) / 2.;
+      dE[a][b] = s;
+    }
+  double CiE = 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) CiE += Ci[a][b] * dE[a][b];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) dECi[a][b] = dE[a][0] * Ci[0][b] + dE[a][1] * Ci[1][b] + dE[a][2] * Ci[2][b];
+  const double llnj_m = llnj - mt.mu;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+      dS[a][b] = mt.lambda * CiE * Ci[a][b] -
+                 2. * llnj_m * (Ci[a][0] * dECi[0][b] + Ci[a][1] * dECi[1][b] + Ci[a][2] * dECi[2][b]);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      double s = 0;
+#pragma unroll
+      for (int m = 0; m < 3; m++) s += gd[a][m] * S[m][b] + F[a][m] * dS[m][b];
+      dP[a][b] = s * w;
+    }
+  pull_back(A, dP, W);
+}
+
+// ------------------------------------------------------------------ Jacobian cache
+// Per quadrature point, the Jacobian action in its cheapest exact algebraic form.
+//
+//   linElas  (10): w, A                      W = A (w sigma(H A))^T-form, as the reference
+//   hyperSS  (11): w, A, s = 1/(1+tr gradu)  dsigma = lambda s tr(g) I + mu (g + g^T)
+//   hyperFS  (17): w, K = A F^-1, b = F F^T (Voigt), lnJ
+//       With gt = H K (spatial gradient of the increment) the reference's
+//       dP = grad(du) S + F dS, S = mu I + (lambda lnJ - mu) C^-1, collapses to
+//         W = w [ mu gt b + lambda tr(gt) I + (mu - lambda lnJ) gt^T ] K^T
+//       (the two (lambda lnJ - mu) gt K K^T terms cancel), ~105 FP64 ops instead of ~580.
+//       Material constants are NOT baked in, so GetDiag_Ceed's smoother-context swap
+//       (matops.c:215-217) keeps working.
+template <int PROB> struct JCache;
+template <> struct JCache<B200_PROB_LINELAS> { static constexpr int N = 10; };
+template <> struct JCache<B200_PROB_HYPERSS> { static constexpr int N = 11; };
+template <> struct JCache<B200_PROB_HYPERFS> { static constexpr int N = 17; };
+
+// qd[10] = qdata, gu[9] = gradu [c][k]  ->  jc[N]
+template <int PROB>
+B200_DI void jcache_point(const double *qd, const double *gu, double *jc) {
+  if (PROB == B200_PROB_LINELAS) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) jc[i] = qd[i];
+  } else if (PROB == B200_PROB_HYPERSS) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) jc[i] = qd[i];
+    jc[10] = 1. / (1. + (gu[0] + gu[4] + gu[8]));
+  } else {
+    double g[3][3], F[3][3], Fi[3][3], e[6];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        g[c][k] = gu[c * 3 + k];
+        F[c][k] = g[c][k] + (c == k ? 1. : 0.);
+      }
+    const double c00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
+    const double c01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
+    const double c02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
+    const double rdet = 1. / (F[0][0] * c00 + F[0][1] * c01 + F[0][2] * c02);
+    Fi[0][0] = c00 * rdet;
+    Fi[1][0] = c01 * rdet;
+    Fi[2][0] = c02 * rdet;
+    Fi[0][1] = (F[0][2] * F[2][1] - F[0][1] * F[2][2]) * rdet;
+    Fi[1][1] = (F[0][0] * F[2][2] - F[0][2] * F[2][0]) * rdet;
+    Fi[2][1] = (F[0][1] * F[2][0] - F[0][0] * F[2][1]) * rdet;
+    Fi[0][2] = (F[0][1] * F[1][2] - F[0][2] * F[1][1]) * rdet;
+    Fi[1][2] = (F[0][2] * F[1][0] - F[0][0] * F[1][2]) * rdet;
+    Fi[2][2] = (F[0][0] * F[1][1] - F[0][1] * F[1][0]) * rdet;
+    jc[0] = qd[0];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        jc[1 + 3 * k + j] = qd[1 + 3 * k] * Fi[0][j] + qd[2 + 3 * k] * Fi[1][j] + qd[3 + 3 * k] * Fi[2][j];
+    const int vj[6] = {0, 1, 2, 1, 0, 0}, vk[6] = {0, 1, 2, 2, 2, 1};
+#pragma unroll
+    for (int m = 0; m < 6; m++)
+      jc[10 + m] = F[vj[m]][0] * F[vk[m]][0] + F[vj[m]][1] * F[vk[m]][1] + F[vj[m]][2] * F[vk[m]][2];
+    jc[16] = log1p_series_shifted(green_lagrange2(g, e)) / 2.;
+  }
+}
+
+// Jacobian action from the cache:  W = J_q(H)
+template <int PROB>
+B200_DI void jacobian_point(const Material &mt, const double *jc, const double (&H)[3][3],
+                            double (&W)[3][3]) {
+  double A[3][3];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) A[m][k] = jc[1 + 3 * m + k];
+  const double w = jc[0];
+  if (PROB == B200_PROB_LINELAS) {
+    linelas_point(mt, w, A, H, W);
+  } else if (PROB == B200_PROB_HYPERSS) {
+    hyperss_df_point(mt, w, A, jc[10], H, W);
+  } else {
+    // A holds K here
+    double gt[3][3], Z[3][3], bm[3][3];
+    const double bv[6] = {jc[10], jc[11], jc[12], jc[13], jc[14], jc[15]};
+    voigt_sym(bv, bm);
+    phys_grad(A, H, gt);  // gt[c][j] = sum_m H[c][m] K[m][j]
+    const double cw = mt.mu * w, bw = (mt.mu - mt.lambda * jc[16]) * w;
+    const double aw = (mt.lambda * w) * (gt[0][0] + gt[1][1] + gt[2][2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        Z[c][j] = cw * (gt[c][0] * bm[0][j] + gt[c][1] * bm[1][j] + gt[c][2] * bm[2][j]) + bw * gt[j][c] +
+                  (c == j ? aw : 0.);
+    pull_back(A, Z, W);  // W[c][k] = sum_m K[k][m] Z[c][m]
+  }
+}
+
+}  // namespace b200

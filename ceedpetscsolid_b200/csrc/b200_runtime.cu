@@ -1,0 +1,200 @@
+// Runtime pieces of the thin C-ABI CUDA layer: device/stream/memory management,
+// CeedVector kernels, index gather/scatter for the global<->local maps and halos.
+#include <string.h>
+
+#include "b200_common.cuh"
+
+namespace b200 {
+cudaStream_t g_stream = 0;
+unsigned long long g_launches = 0;
+static char g_err[512] = "";
+
+int set_error(cudaError_t e, const char *what) {
+  snprintf(g_err, sizeof g_err, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+int set_error_msg(const char *msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return 999;
+}
+
+static inline int grid_for(size_t n, int nt) {
+  size_t nb = (n + nt - 1) / nt;
+  const size_t cap = 148 * 32;
+  return (int)(nb > cap ? cap : (nb ? nb : 1));
+}
+
+#define GRID_STRIDE(i, n) \
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (n); i += (size_t)gridDim.x * blockDim.x)
+
+__global__ void k_set(double *d, double v, size_t n) { GRID_STRIDE(i, n) d[i] = v; }
+__global__ void k_recip(double *d, size_t n) {
+  GRID_STRIDE(i, n) { const double v = d[i]; d[i] = fabs(v) > 1e-14 ? 1.0 / v : v; }  // CeedVectorReciprocal guards tiny entries
+}
+__global__ void k_scale(double *d, double a, size_t n) { GRID_STRIDE(i, n) d[i] *= a; }
+__global__ void k_axpy(double *y, double a, const double *x, size_t n) { GRID_STRIDE(i, n) y[i] += a * x[i]; }
+__global__ void k_aypx(double *y, double a, const double *x, size_t n) { GRID_STRIDE(i, n) y[i] = x[i] + a * y[i]; }
+__global__ void k_axpby(double *z, double a, const double *x, double b, const double *y, size_t n) {
+  GRID_STRIDE(i, n) z[i] = a * x[i] + b * y[i];
+}
+__global__ void k_pmult(double *w, const double *x, const double *y, size_t n) { GRID_STRIDE(i, n) w[i] = x[i] * y[i]; }
+__global__ void k_gather(double *dst, const double *src, const int *idx, size_t n) { GRID_STRIDE(i, n) dst[i] = src[idx[i]]; }
+__global__ void k_scatter_set(double *dst, const int *idx, const double *src, size_t n) { GRID_STRIDE(i, n) dst[idx[i]] = src[i]; }
+__global__ void k_scatter_add(double *dst, const int *idx, const double *src, size_t n) {
+  GRID_STRIDE(i, n) atomicAdd(dst + idx[i], src[i]);
+}
+__global__ void k_mask_zero(double *d, const int *idx, size_t n) { GRID_STRIDE(i, n) d[idx[i]] = 0.0; }
+
+// deterministic two-pass reductions (fixed grid, fixed tree): mode 0 dot, 1 sum|x|, 2 max|x|
+template <int MODE>
+__global__ void k_reduce_partial(const double *x, const double *y, size_t n, double *partial) {
+  __shared__ double sh[256];
+  double s = 0;
+  GRID_STRIDE(i, n) {
+    if (MODE == 0) s += x[i] * y[i];
+    else if (MODE == 1) s += fabs(x[i]);
+    else s = fmax(s, fabs(x[i]));
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] = MODE == 2 ? fmax(sh[threadIdx.x], sh[threadIdx.x + w]) : sh[threadIdx.x] + sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+template <int MODE>
+__global__ void k_reduce_final(const double *partial, int np, double *out) {
+  __shared__ double sh[256];
+  double s = 0;
+  for (int i = threadIdx.x; i < np; i += 256) s = MODE == 2 ? fmax(s, partial[i]) : s + partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] = MODE == 2 ? fmax(sh[threadIdx.x], sh[threadIdx.x + w]) : sh[threadIdx.x] + sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+static double *g_partial = nullptr;  // 1024 partials + 1 result
+static const int kReduceBlocks = 592;  // 148 SMs x 4
+
+template <int MODE>
+static int reduce(const double *x, const double *y, size_t n, double *dresult) {
+  if (!g_partial) B200_CHECK(cudaMalloc(&g_partial, sizeof(double) * 1032));
+  k_reduce_partial<MODE><<<kReduceBlocks, 256, 0, g_stream>>>(x, y, n, g_partial);
+  B200_LAUNCH_CHECK("k_reduce_partial");
+  k_reduce_final<MODE><<<1, 256, 0, g_stream>>>(g_partial, kReduceBlocks, dresult);
+  B200_LAUNCH_CHECK("k_reduce_final");
+  return 0;
+}
+template <int MODE>
+static int reduce_host(const double *x, const double *y, size_t n, double *hresult) {
+  if (!g_partial) B200_CHECK(cudaMalloc(&g_partial, sizeof(double) * 1032));
+  if (int rc = reduce<MODE>(x, y, n, g_partial + 1024)) return rc;
+  B200_CHECK(cudaMemcpyAsync(hresult, g_partial + 1024, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  B200_CHECK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_device_count(int *count) { B200_CHECK(cudaGetDeviceCount(count)); return 0; }
+int b200_set_device(int dev) { B200_CHECK(cudaSetDevice(dev)); return 0; }
+int b200_get_device(int *dev) { B200_CHECK(cudaGetDevice(dev)); return 0; }
+int b200_set_stream(void *s) { g_stream = (cudaStream_t)s; return 0; }
+void *b200_get_stream(void) { return (void *)g_stream; }
+int b200_sync(void) { B200_CHECK(cudaStreamSynchronize(g_stream)); return 0; }
+const char *b200_last_error(void) { return g_err; }
+int b200_device_name(char *buf, int len) {
+  int dev; cudaDeviceProp p;
+  B200_CHECK(cudaGetDevice(&dev));
+  B200_CHECK(cudaGetDeviceProperties(&p, dev));
+  snprintf(buf, len, "%s (sm_%d%d, %d SMs)", p.name, p.major, p.minor, p.multiProcessorCount);
+  return 0;
+}
+int b200_sm_count(int *count) {
+  int dev;
+  B200_CHECK(cudaGetDevice(&dev));
+  B200_CHECK(cudaDeviceGetAttribute(count, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
+int b200_malloc(void **dptr, size_t bytes) { B200_CHECK(cudaMalloc(dptr, bytes ? bytes : 8)); return 0; }
+int b200_free(void *dptr) { if (dptr) B200_CHECK(cudaFree(dptr)); return 0; }
+int b200_malloc_host(void **hptr, size_t bytes) { B200_CHECK(cudaMallocHost(hptr, bytes ? bytes : 8)); return 0; }
+int b200_free_host(void *hptr) { if (hptr) B200_CHECK(cudaFreeHost(hptr)); return 0; }
+int b200_memset(void *dptr, int value, size_t bytes) { B200_CHECK(cudaMemsetAsync(dptr, value, bytes, g_stream)); return 0; }
+int b200_memcpy_h2d(void *d, const void *h, size_t bytes) {
+  B200_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g_stream));
+  return 0;
+}
+int b200_memcpy_d2h(void *h, const void *d, size_t bytes) {
+  B200_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, g_stream));
+  B200_CHECK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+int b200_memcpy_d2d(void *d, const void *s, size_t bytes) {
+  B200_CHECK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, g_stream));
+  return 0;
+}
+int b200_pointer_is_device(const void *p, int *is_device) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); *is_device = 0; return 0; }
+  *is_device = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+  return 0;
+}
+
+unsigned long long b200_launch_count(void) { return g_launches; }
+void b200_launch_count_reset(void) { g_launches = 0; }
+
+#define VEC_KERNEL(call, n)                          \
+  do {                                               \
+    if ((n) == 0) return 0;                          \
+    call;                                            \
+    B200_LAUNCH_CHECK(#call);                        \
+    return 0;                                        \
+  } while (0)
+
+int b200_vec_set(double *d, double v, size_t n) {
+  if (v == 0.0) { if (n) B200_CHECK(cudaMemsetAsync(d, 0, n * sizeof(double), g_stream)); return 0; }
+  VEC_KERNEL((k_set<<<grid_for(n, 256), 256, 0, g_stream>>>(d, v, n)), n);
+}
+int b200_vec_reciprocal(double *d, size_t n) { VEC_KERNEL((k_recip<<<grid_for(n, 256), 256, 0, g_stream>>>(d, n)), n); }
+int b200_vec_scale(double *d, double a, size_t n) { VEC_KERNEL((k_scale<<<grid_for(n, 256), 256, 0, g_stream>>>(d, a, n)), n); }
+int b200_vec_axpy(double *y, double a, const double *x, size_t n) { VEC_KERNEL((k_axpy<<<grid_for(n, 256), 256, 0, g_stream>>>(y, a, x, n)), n); }
+int b200_vec_aypx(double *y, double a, const double *x, size_t n) { VEC_KERNEL((k_aypx<<<grid_for(n, 256), 256, 0, g_stream>>>(y, a, x, n)), n); }
+int b200_vec_axpby(double *z, double a, const double *x, double b, const double *y, size_t n) {
+  VEC_KERNEL((k_axpby<<<grid_for(n, 256), 256, 0, g_stream>>>(z, a, x, b, y, n)), n);
+}
+int b200_vec_pointwise_mult(double *w, const double *x, const double *y, size_t n) {
+  VEC_KERNEL((k_pmult<<<grid_for(n, 256), 256, 0, g_stream>>>(w, x, y, n)), n);
+}
+int b200_vec_dot(const double *x, const double *y, size_t n, double *dresult) { return reduce<0>(x, y, n, dresult); }
+int b200_vec_dot_host(const double *x, const double *y, size_t n, double *hresult) { return reduce_host<0>(x, y, n, hresult); }
+int b200_vec_norm_host(const double *x, size_t n, int norm_type, double *hresult) {
+  int rc;
+  if (norm_type == 0) return reduce_host<1>(x, x, n, hresult);
+  if (norm_type == 2) return reduce_host<2>(x, x, n, hresult);
+  rc = reduce_host<0>(x, x, n, hresult);
+  if (!rc) *hresult = sqrt(*hresult);
+  return rc;
+}
+int b200_gather(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_gather<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
+int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_set<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
+int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_add<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
+int b200_mask_zero(double *d, const int *idx, size_t n) { VEC_KERNEL((k_mask_zero<<<grid_for(n, 256), 256, 0, g_stream>>>(d, idx, n)), n); }
+
+int b200_elems_per_block(int Q) { return elems_per_block(Q); }
+int b200_strided_layout_q(int elemsize) {
+  for (int Q = 2; Q <= 8; Q++)
+    if (Q * Q * Q == elemsize) return Q;
+  return 0;
+}
+
+}  // extern "C"

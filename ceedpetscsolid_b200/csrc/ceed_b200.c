@@ -1,0 +1,1102 @@
+/* ceed_b200.c -- libCEED-compatible front-end + the "/gpu/b200" backend, in C99 over the
+ * thin C-ABI CUDA layer (include/b200_kernels.h).
+ *
+ * What it mirrors (libCEED is not vendored in the reference; its call sites are):
+ *   - the user API the reference calls (/root/reference/src/setuplibceed.c,
+ *     src/matops.c, src/misc.c, elasticity.c)
+ *   - libCEED interface semantics: reference-counted objects, CeedOperatorApply = zero every
+ *     output vector (active and passive) then ApplyAdd, fields matched by NAME between
+ *     CeedQFunctionAdd{In,Out}put and CeedOperatorSetField, CEED_USE_POINTER borrows.
+ *
+ * Operator execution:
+ *   FUSED     residual / Jacobian operators of the three material models -> one kernel
+ *             (b200_apply_residual / b200_apply_jacobian); transfer operators -> b200_apply_transfer
+ *   GENERIC   everything else: restriction, basis and QFunction kernels chained on the device
+ * There is no CPU fallback: a QFunction the backend does not recognise is an error.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b200_kernels.h"
+#include "ceed/ceed.h"
+
+#define MAXF 8
+#define CEED_B200_RESOURCE "/gpu/b200"
+
+/* ------------------------------------------------------------------ objects */
+typedef struct JCacheEntry {
+  CeedVector qdata, gradu;
+  int problem, nelem, Q;
+  uint64_t vq, vg;
+  double *d;
+  struct JCacheEntry *next;
+} JCacheEntry;
+
+struct Ceed_private {
+  char resource[128];
+  int refcount;
+  CeedErrorHandler eh;
+  char errmsg[1024];
+  JCacheEntry *jcaches;
+};
+
+struct CeedVector_private {
+  Ceed ceed;
+  int refcount;
+  CeedInt length;
+  double *h, *d;
+  int h_owned, d_owned, h_valid, d_valid;
+  uint64_t version;
+};
+
+struct CeedElemRestriction_private {
+  Ceed ceed;
+  int refcount;
+  CeedInt nelem, elemsize, ncomp, compstride, lsize;
+  int strided, backend_strides, layout_q, offsets_borrowed;
+  CeedInt strides[3];
+  int *d_offsets;
+};
+
+struct CeedBasis_private {
+  Ceed ceed;
+  int refcount;
+  CeedInt dim, ncomp, P, Q;
+  double *interp1d, *grad1d, *qref1d, *qweight1d;        /* host */
+  double *d_interp1d, *d_grad1d, *d_qweight1d;           /* device, lazy */
+};
+
+typedef struct {
+  char name[64];
+  CeedInt size;
+  CeedEvalMode emode;
+} QFField;
+
+struct CeedQFunction_private {
+  Ceed ceed;
+  int refcount;
+  CeedInt vlength;
+  CeedQFunctionUser f;
+  char source[512], name[128];
+  int qf_id;
+  int nin, nout;
+  QFField in[MAXF], out[MAXF];
+  void *ctx;
+  size_t ctxsize;
+  int identity_size;
+};
+
+typedef struct {
+  int set;
+  CeedElemRestriction r;
+  CeedBasis b;
+  CeedVector v;
+} OpField;
+
+enum { OP_UNSET = 0, OP_GENERIC, OP_FUSED_RESIDUAL, OP_FUSED_JACOBIAN, OP_FUSED_TRANSFER };
+
+struct CeedOperator_private {
+  Ceed ceed;
+  int refcount;
+  CeedQFunction qf;
+  OpField in[MAXF], out[MAXF];
+  int kind, problem;
+  int composite, nsubs;
+  CeedOperator subs[MAXF];
+  /* generic-path work buffers (device), grown on demand */
+  double *ebuf[2 * MAXF], *qbuf[2 * MAXF];
+  size_t ebytes[2 * MAXF], qbytes[2 * MAXF];
+};
+
+/* ------------------------------------------------------------------ sentinels */
+static struct CeedBasis_private basis_collocated_;
+static struct CeedVector_private vector_active_, vector_none_;
+static struct CeedElemRestriction_private rstr_none_;
+static struct CeedQFunction_private qf_none_;
+static CeedRequest req_immediate_, req_ordered_;
+const CeedInt CEED_STRIDES_BACKEND[3] = {0, 0, 0};
+const CeedBasis CEED_BASIS_COLLOCATED = &basis_collocated_;
+const CeedVector CEED_VECTOR_ACTIVE = &vector_active_;
+const CeedVector CEED_VECTOR_NONE = &vector_none_;
+const CeedElemRestriction CEED_ELEMRESTRICTION_NONE = &rstr_none_;
+const CeedQFunction CEED_QFUNCTION_NONE = &qf_none_;
+CeedRequest *const CEED_REQUEST_IMMEDIATE = &req_immediate_;
+CeedRequest *const CEED_REQUEST_ORDERED = &req_ordered_;
+const char *const CeedMemTypes[] = {"host", "device", 0};
+const char *const CeedEvalModes[] = {"none", "interpolation", "gradient", "", "divergence", "", "", "",
+                                     "curl", "", "", "", "", "", "", "", "quadrature weights", 0};
+
+/* ------------------------------------------------------------------ errors */
+static char g_last_error[1024];
+static CeedErrorHandler g_default_eh = NULL; /* NULL = CeedErrorAbort (upstream default) */
+
+int CeedErrorAbort(Ceed ceed, const char *file, int line, const char *func, int ecode, const char *format,
+                   va_list *args) {
+  (void)ceed;
+  fprintf(stderr, "%s:%d in %s(): ", file, line, func);
+  vfprintf(stderr, format, *args);
+  fprintf(stderr, "\nAborted (libceed_b200, error %d)\n", ecode);
+  abort();
+  return ecode;
+}
+int CeedErrorReturn(Ceed ceed, const char *file, int line, const char *func, int ecode, const char *format,
+                    va_list *args) {
+  (void)ceed; (void)file; (void)line; (void)func; (void)format; (void)args;
+  return ecode;
+}
+int CeedErrorStore(Ceed ceed, const char *file, int line, const char *func, int ecode, const char *format,
+                   va_list *args) {
+  char *dst = ceed ? ceed->errmsg : g_last_error;
+  int n = snprintf(dst, 1024, "%s:%d in %s(): ", file, line, func);
+  if (n < 1024) vsnprintf(dst + n, 1024 - n, format, *args);
+  if (ceed) memcpy(g_last_error, dst, 1024);
+  return ecode;
+}
+static int CeedErrorImpl(Ceed ceed, const char *file, int line, const char *func, int ecode, const char *format, ...) {
+  va_list args;
+  va_start(args, format);
+  CeedErrorHandler eh = ceed && ceed->eh ? ceed->eh : (g_default_eh ? g_default_eh : CeedErrorAbort);
+  int rc = eh(ceed, file, line, func, ecode, format, &args);
+  va_end(args);
+  return rc;
+}
+#define CeedError(ceed, ecode, ...) CeedErrorImpl((ceed), __FILE__, __LINE__, __func__, (ecode), __VA_ARGS__)
+#define CeedChk(ierr) do { int ierr_ = (ierr); if (ierr_) return ierr_; } while (0)
+/* thin-layer call: turn a CUDA-layer failure into a Ceed error */
+#define B2(ceed, call) do { int rc_ = (call); if (rc_) return CeedError((ceed), rc_, "%s: %s", #call, b200_last_error()); } while (0)
+
+/* ceed == NULL sets the process-wide default used by CeedInit failures and new Ceed objects */
+int CeedSetErrorHandler(Ceed ceed, CeedErrorHandler handler) {
+  if (ceed) ceed->eh = handler;
+  else g_default_eh = handler;
+  return 0;
+}
+int CeedGetErrorMessage(Ceed ceed, const char **errmsg) { *errmsg = ceed ? ceed->errmsg : g_last_error; return 0; }
+int CeedResetErrorMessage(Ceed ceed, const char **errmsg) {
+  if (ceed) ceed->errmsg[0] = 0;
+  g_last_error[0] = 0;
+  if (errmsg) *errmsg = NULL;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ Ceed */
+int CeedInit(const char *resource, Ceed *ceed) {
+  *ceed = NULL;
+  if (!resource || strncmp(resource, CEED_B200_RESOURCE, strlen(CEED_B200_RESOURCE)))
+    return CeedError(NULL, 1, "No suitable backend: %s (this library serves only %s; there is no CPU fallback)",
+                     resource ? resource : "(null)", CEED_B200_RESOURCE);
+  int ndev = 0;
+  if (b200_device_count(&ndev) || ndev < 1)
+    return CeedError(NULL, 2, "%s: no CUDA device visible (%s)", CEED_B200_RESOURCE, b200_last_error());
+  /* optional "/gpu/b200:device_id=N" */
+  const char *dv = strstr(resource, "device_id=");
+  if (dv) {
+    int id = atoi(dv + 10);
+    if (id < 0 || id >= ndev) return CeedError(NULL, 2, "%s: device_id %d out of range", CEED_B200_RESOURCE, id);
+    B2(NULL, b200_set_device(id));
+  }
+  Ceed c = (Ceed)calloc(1, sizeof *c);
+  if (!c) return CeedError(NULL, 3, "out of memory");
+  snprintf(c->resource, sizeof c->resource, "%s", resource);
+  c->refcount = 1;
+  c->eh = g_default_eh ? g_default_eh : CeedErrorAbort;
+  *ceed = c;
+  return 0;
+}
+
+static void jcache_drop_for(Ceed ceed, CeedVector v) {
+  JCacheEntry **p = &ceed->jcaches;
+  while (*p) {
+    if (!v || (*p)->qdata == v || (*p)->gradu == v) {
+      JCacheEntry *dead = *p;
+      *p = dead->next;
+      b200_free(dead->d);
+      free(dead);
+    } else {
+      p = &(*p)->next;
+    }
+  }
+}
+
+int CeedDestroy(Ceed *ceed) {
+  if (!ceed || !*ceed) return 0;
+  if (--(*ceed)->refcount > 0) { *ceed = NULL; return 0; }
+  jcache_drop_for(*ceed, NULL);
+  free(*ceed);
+  *ceed = NULL;
+  return 0;
+}
+int CeedGetResource(Ceed ceed, const char **resource) { *resource = ceed->resource; return 0; }
+int CeedGetPreferredMemType(Ceed ceed, CeedMemType *type) { (void)ceed; *type = CEED_MEM_DEVICE; return 0; }
+int CeedIsDeterministic(Ceed ceed, int *isDeterministic) { (void)ceed; *isDeterministic = 0; return 0; }
+int CeedB200SetStream(Ceed ceed, void *s) { B2(ceed, b200_set_stream(s)); return 0; }
+int CeedB200Synchronize(Ceed ceed) { B2(ceed, b200_sync()); return 0; }
+unsigned long long CeedB200LaunchCount(void) { return b200_launch_count(); }
+void CeedB200LaunchCountReset(void) { b200_launch_count_reset(); }
+
+/* ------------------------------------------------------------------ CeedVector */
+int CeedVectorCreate(Ceed ceed, CeedInt len, CeedVector *vec) {
+  if (len < 0) return CeedError(ceed, 1, "CeedVectorCreate: negative length %d", len);
+  CeedVector v = (CeedVector)calloc(1, sizeof *v);
+  if (!v) return CeedError(ceed, 3, "out of memory");
+  v->ceed = ceed;
+  ceed->refcount++;
+  v->refcount = 1;
+  v->length = len;
+  *vec = v;
+  return 0;
+}
+
+static size_t vbytes(CeedVector v) { return (size_t)v->length * sizeof(double); }
+
+static int vec_alloc(CeedVector v, CeedMemType m) {
+  if (m == CEED_MEM_HOST && !v->h) {
+    v->h = (double *)malloc(vbytes(v) ? vbytes(v) : 8);
+    if (!v->h) return CeedError(v->ceed, 3, "out of host memory (%zu bytes)", vbytes(v));
+    v->h_owned = 1;
+  } else if (m == CEED_MEM_DEVICE && !v->d) {
+    B2(v->ceed, b200_malloc((void **)&v->d, vbytes(v)));
+    v->d_owned = 1;
+  }
+  return 0;
+}
+
+static int vec_release(CeedVector v, CeedMemType m) {
+  if (m == CEED_MEM_HOST) {
+    if (v->h && v->h_owned) free(v->h);
+    v->h = NULL; v->h_owned = 0; v->h_valid = 0;
+  } else {
+    if (v->d && v->d_owned) B2(v->ceed, b200_free(v->d));
+    v->d = NULL; v->d_owned = 0; v->d_valid = 0;
+  }
+  return 0;
+}
+
+static int vec_sync(CeedVector v, CeedMemType m) {
+  if (m == CEED_MEM_HOST) {
+    if (v->h_valid) return 0;
+    if (!v->d_valid) return CeedError(v->ceed, 4, "CeedVector has no valid data (set it with CeedVectorSetArray/SetValue)");
+    CeedChk(vec_alloc(v, CEED_MEM_HOST));
+    B2(v->ceed, b200_memcpy_d2h(v->h, v->d, vbytes(v)));
+    v->h_valid = 1;
+  } else {
+    if (v->d_valid) return 0;
+    if (!v->h_valid) return CeedError(v->ceed, 4, "CeedVector has no valid data (set it with CeedVectorSetArray/SetValue)");
+    CeedChk(vec_alloc(v, CEED_MEM_DEVICE));
+    B2(v->ceed, b200_memcpy_h2d(v->d, v->h, vbytes(v)));
+    v->d_valid = 1;
+  }
+  return 0;
+}
+
+/* backend-internal device access */
+static int vec_dev_read(CeedVector v, const double **p) { CeedChk(vec_sync(v, CEED_MEM_DEVICE)); *p = v->d; return 0; }
+static int vec_dev_write(CeedVector v, double **p) { /* contents undefined: caller overwrites everything */
+  CeedChk(vec_alloc(v, CEED_MEM_DEVICE));
+  v->d_valid = 1; v->h_valid = 0; v->version++;
+  *p = v->d;
+  return 0;
+}
+static int vec_dev_rw(CeedVector v, double **p) {
+  CeedChk(vec_sync(v, CEED_MEM_DEVICE));
+  v->h_valid = 0; v->version++;
+  *p = v->d;
+  return 0;
+}
+
+int CeedVectorSetArray(CeedVector vec, CeedMemType mtype, CeedCopyMode cmode, CeedScalar *array) {
+  Ceed ceed = vec->ceed;
+  if (!array) return CeedError(ceed, 1, "CeedVectorSetArray: NULL array");
+  if (mtype == CEED_MEM_HOST) {
+    if (cmode == CEED_COPY_VALUES) {
+      if (vec->h && !vec->h_owned) { vec->h = NULL; }
+      CeedChk(vec_alloc(vec, CEED_MEM_HOST));
+      memcpy(vec->h, array, vbytes(vec));
+    } else {
+      CeedChk(vec_release(vec, CEED_MEM_HOST));
+      vec->h = array;
+      vec->h_owned = cmode == CEED_OWN_POINTER;
+    }
+    vec->h_valid = 1; vec->d_valid = 0;
+  } else {
+    if (cmode == CEED_COPY_VALUES) {
+      if (vec->d && !vec->d_owned) { vec->d = NULL; }
+      CeedChk(vec_alloc(vec, CEED_MEM_DEVICE));
+      B2(ceed, b200_memcpy_d2d(vec->d, array, vbytes(vec)));
+    } else {
+      CeedChk(vec_release(vec, CEED_MEM_DEVICE));
+      vec->d = array;
+      vec->d_owned = cmode == CEED_OWN_POINTER;
+    }
+    vec->d_valid = 1; vec->h_valid = 0;
+  }
+  vec->version++;
+  return 0;
+}
+
+/* Ends a borrow (matops.c:49-50): the data is made current in `mtype` memory first, so a
+ * host-borrowed output receives the device result here. */
+int CeedVectorTakeArray(CeedVector vec, CeedMemType mtype, CeedScalar **array) {
+  if (!vec->h_valid && !vec->d_valid) {
+    if (array) *array = NULL;
+    return 0;
+  }
+  CeedChk(vec_sync(vec, mtype));
+  if (mtype == CEED_MEM_HOST) {
+    if (array) *array = vec->h;
+    else if (vec->h_owned) free(vec->h);
+    vec->h = NULL; vec->h_owned = 0;
+  } else {
+    /* stream-ordered hand-back: work queued on the backend stream must be visible to the
+       caller's next stream-ordered consumer; both use the same stream. */
+    if (array) *array = vec->d;
+    else if (vec->d_owned) B2(vec->ceed, b200_free(vec->d));
+    vec->d = NULL; vec->d_owned = 0;
+  }
+  vec->h_valid = vec->d_valid = 0;
+  vec->version++;
+  return 0;
+}
+
+int CeedVectorSetValue(CeedVector vec, CeedScalar value) {
+  double *d;
+  CeedChk(vec_dev_write(vec, &d));
+  B2(vec->ceed, b200_vec_set(d, value, (size_t)vec->length));
+  return 0;
+}
+int CeedVectorSyncArray(CeedVector vec, CeedMemType mtype) { return vec_sync(vec, mtype); }
+int CeedVectorGetArray(CeedVector vec, CeedMemType mtype, CeedScalar **array) {
+  CeedChk(vec_sync(vec, mtype));
+  if (mtype == CEED_MEM_HOST) { vec->d_valid = 0; *array = vec->h; }
+  else { vec->h_valid = 0; *array = vec->d; }
+  vec->version++;
+  return 0;
+}
+int CeedVectorGetArrayRead(CeedVector vec, CeedMemType mtype, const CeedScalar **array) {
+  CeedChk(vec_sync(vec, mtype));
+  *array = mtype == CEED_MEM_HOST ? vec->h : vec->d;
+  return 0;
+}
+int CeedVectorRestoreArray(CeedVector vec, CeedScalar **array) { (void)vec; if (array) *array = NULL; return 0; }
+int CeedVectorRestoreArrayRead(CeedVector vec, const CeedScalar **array) { (void)vec; if (array) *array = NULL; return 0; }
+int CeedVectorNorm(CeedVector vec, CeedNormType type, CeedScalar *norm) {
+  const double *d;
+  CeedChk(vec_dev_read(vec, &d));
+  B2(vec->ceed, b200_vec_norm_host(d, (size_t)vec->length, (int)type, norm));
+  return 0;
+}
+int CeedVectorReciprocal(CeedVector vec) {
+  double *d;
+  CeedChk(vec_dev_rw(vec, &d));
+  B2(vec->ceed, b200_vec_reciprocal(d, (size_t)vec->length));
+  return 0;
+}
+int CeedVectorGetLength(CeedVector vec, CeedInt *length) { *length = vec->length; return 0; }
+int CeedVectorDestroy(CeedVector *vec) {
+  if (!vec || !*vec) return 0;
+  CeedVector v = *vec;
+  *vec = NULL;
+  if (v == CEED_VECTOR_ACTIVE || v == CEED_VECTOR_NONE) return 0;
+  if (--v->refcount > 0) return 0;
+  jcache_drop_for(v->ceed, v);
+  vec_release(v, CEED_MEM_HOST);
+  vec_release(v, CEED_MEM_DEVICE);
+  Ceed c = v->ceed;
+  free(v);
+  return CeedDestroy(&c);
+}
+
+/* ------------------------------------------------------------------ CeedElemRestriction */
+int CeedElemRestrictionCreate(Ceed ceed, CeedInt nelem, CeedInt elemsize, CeedInt ncomp, CeedInt compstride,
+                              CeedInt lsize, CeedMemType mtype, CeedCopyMode cmode, const CeedInt *offsets,
+                              CeedElemRestriction *rstr) {
+  if (!offsets) return CeedError(ceed, 1, "CeedElemRestrictionCreate: NULL offsets");
+  CeedElemRestriction r = (CeedElemRestriction)calloc(1, sizeof *r);
+  if (!r) return CeedError(ceed, 3, "out of memory");
+  r->ceed = ceed; ceed->refcount++; r->refcount = 1;
+  r->nelem = nelem; r->elemsize = elemsize; r->ncomp = ncomp; r->compstride = compstride; r->lsize = lsize;
+  const size_t n = (size_t)nelem * elemsize;
+  if (mtype == CEED_MEM_HOST) {
+    for (size_t i = 0; i < n; i++) {
+      const long long hi = (long long)offsets[i] + (long long)(ncomp - 1) * compstride;
+      if (offsets[i] < 0 || hi >= lsize) {
+        free(r); ceed->refcount--;
+        return CeedError(ceed, 1, "CeedElemRestrictionCreate: offset %d at position %zu out of range [0,%d)", offsets[i], i, lsize);
+      }
+    }
+    B2(ceed, b200_malloc((void **)&r->d_offsets, n * sizeof(int)));
+    B2(ceed, b200_memcpy_h2d(r->d_offsets, offsets, n * sizeof(int)));
+    B2(ceed, b200_sync());  /* caller may free its array right away (setuplibceed.c:235-237) */
+    if (cmode == CEED_OWN_POINTER) free((void *)offsets);
+  } else {
+    if (cmode == CEED_COPY_VALUES) {
+      B2(ceed, b200_malloc((void **)&r->d_offsets, n * sizeof(int)));
+      B2(ceed, b200_memcpy_d2d(r->d_offsets, offsets, n * sizeof(int)));
+    } else {
+      r->d_offsets = (int *)offsets; /* USE/OWN device pointer: kept, never freed here unless owned */
+      r->offsets_borrowed = cmode == CEED_USE_POINTER;
+    }
+  }
+  *rstr = r;
+  return 0;
+}
+
+int CeedElemRestrictionCreateStrided(Ceed ceed, CeedInt nelem, CeedInt elemsize, CeedInt ncomp, CeedInt lsize,
+                                     const CeedInt strides[3], CeedElemRestriction *rstr) {
+  CeedElemRestriction r = (CeedElemRestriction)calloc(1, sizeof *r);
+  if (!r) return CeedError(ceed, 3, "out of memory");
+  r->ceed = ceed; ceed->refcount++; r->refcount = 1;
+  r->nelem = nelem; r->elemsize = elemsize; r->ncomp = ncomp; r->compstride = 0; r->lsize = lsize;
+  r->strided = 1;
+  if (strides == CEED_STRIDES_BACKEND || (strides[0] == 0 && strides[1] == 0 && strides[2] == 0)) {
+    r->backend_strides = 1;
+    r->layout_q = b200_strided_layout_q(elemsize);  /* q-blocked when elemsize = Q^3 */
+    r->strides[0] = 1; r->strides[1] = elemsize; r->strides[2] = elemsize * ncomp; /* plain layout otherwise */
+  } else {
+    memcpy(r->strides, strides, 3 * sizeof(CeedInt));
+  }
+  if ((long long)nelem * elemsize * ncomp > lsize) {
+    free(r); ceed->refcount--;
+    return CeedError(ceed, 1, "CeedElemRestrictionCreateStrided: lsize %d too small for %d x %d x %d", lsize, nelem, elemsize, ncomp);
+  }
+  *rstr = r;
+  return 0;
+}
+
+int CeedElemRestrictionCreateVector(CeedElemRestriction rstr, CeedVector *lvec, CeedVector *evec) {
+  if (lvec) CeedChk(CeedVectorCreate(rstr->ceed, rstr->lsize, lvec));
+  if (evec) CeedChk(CeedVectorCreate(rstr->ceed, rstr->nelem * rstr->elemsize * rstr->ncomp, evec));
+  return 0;
+}
+
+static int rstr_apply_raw(CeedElemRestriction r, int transpose, const double *in, double *out) {
+  if (r->strided == 1)
+    B2(r->ceed, b200_restrict_strided(transpose, r->nelem, r->elemsize, r->ncomp, r->backend_strides ? r->layout_q : 0,
+                                      r->strides[0], r->strides[1], r->strides[2], in, out));
+  else
+    B2(r->ceed, b200_restrict_offsets(transpose, r->nelem, r->elemsize, r->ncomp, r->compstride, r->d_offsets, in, out));
+  return 0;
+}
+
+/* NOTRANSPOSE: ru = E u (overwrites);  TRANSPOSE: ru += E^T u  (upstream semantics) */
+int CeedElemRestrictionApply(CeedElemRestriction rstr, CeedTransposeMode tmode, CeedVector u, CeedVector ru,
+                             CeedRequest *request) {
+  (void)request;
+  const double *in;
+  double *out;
+  CeedChk(vec_dev_read(u, &in));
+  if (tmode == CEED_NOTRANSPOSE) CeedChk(vec_dev_write(ru, &out));
+  else CeedChk(vec_dev_rw(ru, &out));
+  return rstr_apply_raw(rstr, tmode == CEED_TRANSPOSE, in, out);
+}
+
+/* misc.c:117-123: transpose-apply of an E-vector of ones into a zeroed L-vector */
+int CeedElemRestrictionGetMultiplicity(CeedElemRestriction rstr, CeedVector mult) {
+  Ceed ceed = rstr->ceed;
+  const size_t n = (size_t)rstr->nelem * rstr->elemsize * rstr->ncomp;
+  double *ones, *m;
+  B2(ceed, b200_malloc((void **)&ones, n * sizeof(double)));
+  B2(ceed, b200_vec_set(ones, 1.0, n));
+  CeedChk(vec_dev_write(mult, &m));
+  B2(ceed, b200_vec_set(m, 0.0, (size_t)mult->length));
+  CeedChk(rstr_apply_raw(rstr, 1, ones, m));
+  B2(ceed, b200_sync());
+  B2(ceed, b200_free(ones));
+  return 0;
+}
+int CeedElemRestrictionGetNumElements(CeedElemRestriction r, CeedInt *n) { *n = r->nelem; return 0; }
+int CeedElemRestrictionGetElementSize(CeedElemRestriction r, CeedInt *n) { *n = r->elemsize; return 0; }
+int CeedElemRestrictionGetLVectorSize(CeedElemRestriction r, CeedInt *n) { *n = r->lsize; return 0; }
+int CeedElemRestrictionGetNumComponents(CeedElemRestriction r, CeedInt *n) { *n = r->ncomp; return 0; }
+int CeedElemRestrictionDestroy(CeedElemRestriction *rstr) {
+  if (!rstr || !*rstr) return 0;
+  CeedElemRestriction r = *rstr;
+  *rstr = NULL;
+  if (r == CEED_ELEMRESTRICTION_NONE) return 0;
+  if (--r->refcount > 0) return 0;
+  if (r->d_offsets && !r->offsets_borrowed) b200_free(r->d_offsets);
+  Ceed c = r->ceed;
+  free(r);
+  return CeedDestroy(&c);
+}
+
+/* ------------------------------------------------------------------ CeedBasis */
+static void legendre_pair(int n, double x, double *Pn, double *Pnm1) {
+  double a = 1.0, b = x;
+  if (n == 0) { *Pn = 1.0; *Pnm1 = 0.0; return; }
+  for (int j = 2; j <= n; j++) { const double c = ((2 * j - 1) * x * b - (j - 1) * a) / j; a = b; b = c; }
+  *Pn = b; *Pnm1 = a;
+}
+
+int CeedGaussQuadrature(CeedInt Q, CeedScalar *x, CeedScalar *w) {
+  const double pi = 4.0 * atan(1.0);
+  for (int i = 0; i <= Q / 2; i++) {
+    double xi = cos(pi * (2 * i + 1) / (2.0 * Q)), p, pm, dp = 1;
+    for (int it = 0; it < 100; it++) {
+      legendre_pair(Q, xi, &p, &pm);
+      dp = (xi * p - pm) * Q / (xi * xi - 1.0);
+      const double step = p / dp;
+      xi -= step;
+      if (fabs(step) < 1e-16 || fabs(p) < 1e-15) break;
+    }
+    legendre_pair(Q, xi, &p, &pm);
+    dp = (xi * p - pm) * Q / (xi * xi - 1.0);
+    w[i] = w[Q - 1 - i] = 2.0 / ((1.0 - xi * xi) * dp * dp);
+    x[i] = -xi; x[Q - 1 - i] = xi;
+  }
+  return 0;
+}
+
+int CeedLobattoQuadrature(CeedInt Q, CeedScalar *x, CeedScalar *w) {
+  const double pi = 4.0 * atan(1.0);
+  const int n = Q - 1;
+  if (Q < 2) return 1;
+  x[0] = -1.0; x[Q - 1] = 1.0;
+  if (w) w[0] = w[Q - 1] = 2.0 / (Q * (double)n);
+  for (int i = 1; i <= n / 2; i++) {
+    double xi = cos(pi * i / n), p, pm;
+    for (int it = 0; it < 100; it++) {
+      legendre_pair(n, xi, &p, &pm);
+      const double dp = (xi * p - pm) * n / (xi * xi - 1.0);
+      const double d2p = (2 * xi * dp - n * (n + 1.0) * p) / (1.0 - xi * xi);
+      const double step = dp / d2p;
+      xi -= step;
+      if (fabs(step) < 1e-16) break;
+    }
+    legendre_pair(n, xi, &p, &pm);
+    if (w) w[i] = w[Q - 1 - i] = 2.0 / (Q * (double)n * p * p);
+    x[i] = -xi; x[Q - 1 - i] = xi;
+  }
+  return 0;
+}
+
+int CeedBasisCreateTensorH1(Ceed ceed, CeedInt dim, CeedInt ncomp, CeedInt P, CeedInt Q, const CeedScalar *interp1d,
+                            const CeedScalar *grad1d, const CeedScalar *qref1d, const CeedScalar *qweight1d,
+                            CeedBasis *basis) {
+  if (dim != 3) return CeedError(ceed, 1, "%s supports dim = 3 tensor bases (got %d)", CEED_B200_RESOURCE, dim);
+  if (P < 1 || Q < 1) return CeedError(ceed, 1, "CeedBasisCreateTensorH1: P, Q must be positive");
+  CeedBasis b = (CeedBasis)calloc(1, sizeof *b);
+  if (!b) return CeedError(ceed, 3, "out of memory");
+  b->ceed = ceed; ceed->refcount++; b->refcount = 1;
+  b->dim = dim; b->ncomp = ncomp; b->P = P; b->Q = Q;
+  b->interp1d = (double *)malloc(sizeof(double) * Q * P);
+  b->grad1d = (double *)malloc(sizeof(double) * Q * P);
+  b->qref1d = (double *)malloc(sizeof(double) * Q);
+  b->qweight1d = (double *)malloc(sizeof(double) * Q);
+  memcpy(b->interp1d, interp1d, sizeof(double) * Q * P);
+  memcpy(b->grad1d, grad1d, sizeof(double) * Q * P);
+  memcpy(b->qref1d, qref1d, sizeof(double) * Q);
+  memcpy(b->qweight1d, qweight1d, sizeof(double) * Q);
+  *basis = b;
+  return 0;
+}
+
+/* GLL nodes; Gauss or GLL quadrature; Lagrange interp/grad by Fornberg's recurrence */
+int CeedBasisCreateTensorH1Lagrange(Ceed ceed, CeedInt dim, CeedInt ncomp, CeedInt P, CeedInt Q, CeedQuadMode qmode,
+                                    CeedBasis *basis) {
+  if (P < 2 || Q < 1 || P > 16 || Q > 16) return CeedError(ceed, 1, "CeedBasisCreateTensorH1Lagrange: need 2 <= P <= 16, 1 <= Q <= 16");
+  double nodes[16], qref[16], qw[16], B[256], D[256];
+  CeedLobattoQuadrature(P, nodes, NULL);
+  if (qmode == CEED_GAUSS) CeedGaussQuadrature(Q, qref, qw);
+  else if (Q >= 2) CeedLobattoQuadrature(Q, qref, qw);
+  else return CeedError(ceed, 1, "Gauss-Lobatto needs Q >= 2");
+  for (int i = 0; i < Q; i++) {
+    double *b = B + i * P, *d = D + i * P;
+    for (int j = 0; j < P; j++) b[j] = d[j] = 0.0;
+    double c1 = 1.0, c3 = nodes[0] - qref[i];
+    b[0] = 1.0;
+    for (int j = 1; j < P; j++) {
+      double c2 = 1.0;
+      const double c4 = c3;
+      c3 = nodes[j] - qref[i];
+      for (int k = 0; k < j; k++) {
+        const double dx = nodes[j] - nodes[k];
+        c2 *= dx;
+        if (k == j - 1) {
+          d[j] = c1 * (b[k] - c4 * d[k]) / c2;
+          b[j] = -c1 * c4 * b[k] / c2;
+        }
+        d[k] = (c3 * d[k] - b[k]) / dx;
+        b[k] = c3 * b[k] / dx;
+      }
+      c1 = c2;
+    }
+  }
+  return CeedBasisCreateTensorH1(ceed, dim, ncomp, P, Q, B, D, qref, qw, basis);
+}
+
+static int basis_device(CeedBasis b) {
+  if (b->d_interp1d) return 0;
+  const size_t n = sizeof(double) * b->Q * b->P;
+  B2(b->ceed, b200_malloc((void **)&b->d_interp1d, n));
+  B2(b->ceed, b200_malloc((void **)&b->d_grad1d, n));
+  B2(b->ceed, b200_malloc((void **)&b->d_qweight1d, sizeof(double) * b->Q));
+  B2(b->ceed, b200_memcpy_h2d(b->d_interp1d, b->interp1d, n));
+  B2(b->ceed, b200_memcpy_h2d(b->d_grad1d, b->grad1d, n));
+  B2(b->ceed, b200_memcpy_h2d(b->d_qweight1d, b->qweight1d, sizeof(double) * b->Q));
+  B2(b->ceed, b200_sync());
+  return 0;
+}
+
+static int emode_to_b200(CeedEvalMode e) { return e == CEED_EVAL_INTERP ? 1 : e == CEED_EVAL_GRAD ? 2 : e == CEED_EVAL_WEIGHT ? 4 : 0; }
+
+static int basis_apply_raw(CeedBasis b, CeedInt nelem, int transpose, CeedEvalMode emode, const double *u, double *v) {
+  const int em = emode_to_b200(emode);
+  if (!em) return CeedError(b->ceed, 1, "CeedBasisApply: eval mode %d not supported by %s", (int)emode, CEED_B200_RESOURCE);
+  CeedChk(basis_device(b));
+  B2(b->ceed, b200_basis_apply(nelem, b->ncomp, b->P, b->Q, b->d_interp1d, b->d_grad1d, b->d_qweight1d, transpose, em, u, v));
+  return 0;
+}
+
+int CeedBasisApply(CeedBasis basis, CeedInt nelem, CeedTransposeMode tmode, CeedEvalMode emode, CeedVector u, CeedVector v) {
+  const double *in = NULL;
+  double *out;
+  if (emode != CEED_EVAL_WEIGHT) CeedChk(vec_dev_read(u, &in));
+  CeedChk(vec_dev_write(v, &out));
+  return basis_apply_raw(basis, nelem, tmode == CEED_TRANSPOSE, emode, in, out);
+}
+int CeedBasisGetNumNodes(CeedBasis b, CeedInt *P) { *P = b->P * b->P * b->P; return 0; }
+int CeedBasisGetNumQuadraturePoints(CeedBasis b, CeedInt *Q) { *Q = b->Q * b->Q * b->Q; return 0; }
+int CeedBasisGetInterp1D(CeedBasis b, const CeedScalar **p) { *p = b->interp1d; return 0; }
+int CeedBasisGetGrad1D(CeedBasis b, const CeedScalar **p) { *p = b->grad1d; return 0; }
+int CeedBasisGetQRef(CeedBasis b, const CeedScalar **p) { *p = b->qref1d; return 0; }
+int CeedBasisGetQWeights(CeedBasis b, const CeedScalar **p) { *p = b->qweight1d; return 0; }
+int CeedBasisDestroy(CeedBasis *basis) {
+  if (!basis || !*basis) return 0;
+  CeedBasis b = *basis;
+  *basis = NULL;
+  if (b == CEED_BASIS_COLLOCATED) return 0;
+  if (--b->refcount > 0) return 0;
+  free(b->interp1d); free(b->grad1d); free(b->qref1d); free(b->qweight1d);
+  b200_free(b->d_interp1d); b200_free(b->d_grad1d); b200_free(b->d_qweight1d);
+  Ceed c = b->ceed;
+  free(b);
+  return CeedDestroy(&c);
+}
+
+/* ------------------------------------------------------------------ CeedQFunction */
+static int qf_lookup(const char *name) {
+  static const struct { const char *n; int id; } table[] = {
+      {"SetupGeo", B200_QF_SETUPGEO},     {"LinElasF", B200_QF_LINELAS_F},   {"LinElasdF", B200_QF_LINELAS_DF},
+      {"HyperSSF", B200_QF_HYPERSS_F},    {"HyperSSdF", B200_QF_HYPERSS_DF}, {"HyperFSF", B200_QF_HYPERFS_F},
+      {"HyperFSdF", B200_QF_HYPERFS_DF},  {"Identity", B200_QF_IDENTITY},    {NULL, 0}};
+  for (int i = 0; table[i].n; i++)
+    if (!strcmp(table[i].n, name)) return table[i].id;
+  return B200_QF_NONE;
+}
+
+int CeedQFunctionCreateInterior(Ceed ceed, CeedInt vlength, CeedQFunctionUser f, const char *source, CeedQFunction *qf) {
+  CeedQFunction q = (CeedQFunction)calloc(1, sizeof *q);
+  if (!q) return CeedError(ceed, 3, "out of memory");
+  q->ceed = ceed; ceed->refcount++; q->refcount = 1;
+  q->vlength = vlength; q->f = f;
+  snprintf(q->source, sizeof q->source, "%s", source ? source : "");
+  const char *colon = strrchr(q->source, ':');
+  snprintf(q->name, sizeof q->name, "%s", colon ? colon + 1 : q->source);
+  q->qf_id = qf_lookup(q->name); /* unknown names are reported when an operator tries to run them */
+  *qf = q;
+  return 0;
+}
+
+int CeedQFunctionCreateIdentity(Ceed ceed, CeedInt size, CeedEvalMode inmode, CeedEvalMode outmode, CeedQFunction *qf) {
+  CeedChk(CeedQFunctionCreateInterior(ceed, 1, NULL, "gallery:Identity", qf));
+  (*qf)->identity_size = size;
+  CeedChk(CeedQFunctionAddInput(*qf, "input", size, inmode));
+  CeedChk(CeedQFunctionAddOutput(*qf, "output", size, outmode));
+  return 0;
+}
+
+static int qf_add(CeedQFunction qf, QFField *arr, int *n, const char *name, CeedInt size, CeedEvalMode emode) {
+  if (*n >= MAXF) return CeedError(qf->ceed, 1, "too many QFunction fields (max %d)", MAXF);
+  snprintf(arr[*n].name, sizeof arr[*n].name, "%s", name);
+  arr[*n].size = size; arr[*n].emode = emode;
+  (*n)++;
+  return 0;
+}
+int CeedQFunctionAddInput(CeedQFunction qf, const char *fieldname, CeedInt size, CeedEvalMode emode) {
+  return qf_add(qf, qf->in, &qf->nin, fieldname, size, emode);
+}
+int CeedQFunctionAddOutput(CeedQFunction qf, const char *fieldname, CeedInt size, CeedEvalMode emode) {
+  if (emode == CEED_EVAL_WEIGHT) return CeedError(qf->ceed, 1, "CEED_EVAL_WEIGHT is not a valid output mode");
+  return qf_add(qf, qf->out, &qf->nout, fieldname, size, emode);
+}
+/* The context stays a caller-owned HOST pointer that is re-read at every apply: the reference
+ * passes sizeof(pointer) instead of sizeof(struct) at setuplibceed.c:826, and swaps the
+ * context around the diagonal assembly (matops.c:215-217,231-232). */
+int CeedQFunctionSetContext(CeedQFunction qf, void *ctx, size_t ctxsize) { qf->ctx = ctx; qf->ctxsize = ctxsize; return 0; }
+int CeedQFunctionDestroy(CeedQFunction *qf) {
+  if (!qf || !*qf) return 0;
+  CeedQFunction q = *qf;
+  *qf = NULL;
+  if (q == CEED_QFUNCTION_NONE) return 0;
+  if (--q->refcount > 0) return 0;
+  Ceed c = q->ceed;
+  free(q);
+  return CeedDestroy(&c);
+}
+
+/* ------------------------------------------------------------------ CeedOperator */
+int CeedOperatorCreate(Ceed ceed, CeedQFunction qf, CeedQFunction dqf, CeedQFunction dqfT, CeedOperator *op) {
+  (void)dqf; (void)dqfT;
+  if (!qf || qf == CEED_QFUNCTION_NONE) return CeedError(ceed, 1, "CeedOperatorCreate: a QFunction is required");
+  CeedOperator o = (CeedOperator)calloc(1, sizeof *o);
+  if (!o) return CeedError(ceed, 3, "out of memory");
+  o->ceed = ceed; ceed->refcount++; o->refcount = 1;
+  o->qf = qf; qf->refcount++;
+  *op = o;
+  return 0;
+}
+int CeedCompositeOperatorCreate(Ceed ceed, CeedOperator *op) {
+  CeedOperator o = (CeedOperator)calloc(1, sizeof *o);
+  if (!o) return CeedError(ceed, 3, "out of memory");
+  o->ceed = ceed; ceed->refcount++; o->refcount = 1; o->composite = 1;
+  *op = o;
+  return 0;
+}
+int CeedCompositeOperatorAddSub(CeedOperator comp, CeedOperator sub) {
+  if (!comp->composite) return CeedError(comp->ceed, 1, "CeedCompositeOperatorAddSub: not a composite operator");
+  if (comp->nsubs >= MAXF) return CeedError(comp->ceed, 1, "too many sub-operators");
+  comp->subs[comp->nsubs++] = sub;
+  sub->refcount++;
+  return 0;
+}
+
+int CeedOperatorSetField(CeedOperator op, const char *fieldname, CeedElemRestriction r, CeedBasis b, CeedVector v) {
+  if (op->composite) return CeedError(op->ceed, 1, "CeedOperatorSetField on a composite operator");
+  OpField *f = NULL;
+  for (int i = 0; i < op->qf->nin && !f; i++)
+    if (!strcmp(op->qf->in[i].name, fieldname)) f = &op->in[i];
+  for (int i = 0; i < op->qf->nout && !f; i++)
+    if (!strcmp(op->qf->out[i].name, fieldname)) f = &op->out[i];
+  if (!f) return CeedError(op->ceed, 1, "CeedOperatorSetField: QFunction %s has no field \"%s\"", op->qf->name, fieldname);
+  if (f->set) return CeedError(op->ceed, 1, "CeedOperatorSetField: field \"%s\" already set", fieldname);
+  f->set = 1; f->r = r; f->b = b; f->v = v;
+  if (r && r != CEED_ELEMRESTRICTION_NONE) r->refcount++;
+  if (b && b != CEED_BASIS_COLLOCATED) b->refcount++;
+  if (v && v != CEED_VECTOR_ACTIVE && v != CEED_VECTOR_NONE) v->refcount++;
+  op->kind = OP_UNSET;
+  return 0;
+}
+
+static int is_tensor3(CeedBasis b) { return b && b != CEED_BASIS_COLLOCATED && b->dim == 3; }
+static int is_qstrided(CeedElemRestriction r, int ncomp, int Q) {
+  return r && r != CEED_ELEMRESTRICTION_NONE && r->strided == 1 && r->backend_strides && r->layout_q == Q && r->ncomp == ncomp;
+}
+static int is_passive(CeedVector v) { return v && v != CEED_VECTOR_ACTIVE && v != CEED_VECTOR_NONE; }
+
+/* classify once all fields are set */
+static int op_setup(CeedOperator op) {
+  CeedQFunction qf = op->qf;
+  for (int i = 0; i < qf->nin; i++)
+    if (!op->in[i].set) return CeedError(op->ceed, 1, "operator field \"%s\" of QFunction %s not set", qf->in[i].name, qf->name);
+  for (int i = 0; i < qf->nout; i++)
+    if (!op->out[i].set) return CeedError(op->ceed, 1, "operator field \"%s\" of QFunction %s not set", qf->out[i].name, qf->name);
+  if (qf->qf_id == B200_QF_NONE)
+    return CeedError(op->ceed, 1,
+                     "%s: QFunction \"%s\" (%s) is not one this backend has a device body for; there is no CPU fallback",
+                     CEED_B200_RESOURCE, qf->name, qf->source);
+  op->kind = OP_GENERIC;
+  const int id = qf->qf_id;
+  const int is_res = id == B200_QF_LINELAS_F || id == B200_QF_HYPERSS_F || id == B200_QF_HYPERFS_F;
+  const int is_jac = id == B200_QF_LINELAS_DF || id == B200_QF_HYPERSS_DF || id == B200_QF_HYPERFS_DF;
+  if (is_res || is_jac) {
+    const int prob = (id == B200_QF_LINELAS_F || id == B200_QF_LINELAS_DF) ? B200_PROB_LINELAS
+                     : (id == B200_QF_HYPERSS_F || id == B200_QF_HYPERSS_DF) ? B200_PROB_HYPERSS : B200_PROB_HYPERFS;
+    const int has_gradu = prob != B200_PROB_LINELAS;
+    const int nin = is_jac && has_gradu ? 3 : 2, nout = is_res && has_gradu ? 2 : 1;
+    int ok = qf->nin == nin && qf->nout == nout;
+    if (ok) {
+      OpField *u = &op->in[0], *qd = &op->in[1], *vv = &op->out[0];
+      ok = qf->in[0].emode == CEED_EVAL_GRAD && qf->in[0].size == 9 && u->v == CEED_VECTOR_ACTIVE && is_tensor3(u->b) &&
+           u->b->ncomp == 3 && u->r && u->r != CEED_ELEMRESTRICTION_NONE && u->r->strided == 0 && u->r->ncomp == 3 &&
+           u->r->compstride == 1 && u->r->elemsize == u->b->P * u->b->P * u->b->P;
+      const int Q = ok ? u->b->Q : 0;
+      ok = ok && b200_fused_supported(u->b->P, Q);
+      ok = ok && qf->in[1].emode == CEED_EVAL_NONE && qf->in[1].size == 10 && is_qstrided(qd->r, 10, Q) &&
+           is_passive(qd->v) && qd->r->nelem == u->r->nelem;
+      ok = ok && qf->out[0].emode == CEED_EVAL_GRAD && qf->out[0].size == 9 && vv->v == CEED_VECTOR_ACTIVE &&
+           vv->r == u->r && (vv->b == u->b || (is_tensor3(vv->b) && vv->b->P == u->b->P && vv->b->Q == Q &&
+                                               !memcmp(vv->b->interp1d, u->b->interp1d, sizeof(double) * Q * u->b->P) &&
+                                               !memcmp(vv->b->grad1d, u->b->grad1d, sizeof(double) * Q * u->b->P)));
+      if (ok && has_gradu) {
+        OpField *g = is_jac ? &op->in[2] : &op->out[1];
+        const QFField *gf = is_jac ? &qf->in[2] : &qf->out[1];
+        ok = gf->emode == CEED_EVAL_NONE && gf->size == 9 && is_qstrided(g->r, 9, Q) && is_passive(g->v) &&
+             g->r->nelem == u->r->nelem;
+      }
+    }
+    if (ok) {
+      op->kind = is_res ? OP_FUSED_RESIDUAL : OP_FUSED_JACOBIAN;
+      op->problem = prob;
+    }
+  } else if (id == B200_QF_IDENTITY && qf->nin == 1 && qf->nout == 1 && qf->identity_size == 3) {
+    /* p-MG transfer (setuplibceed.c:847-863): prolong = coarse INTERP(basisCtoF) -> fine NONE;
+       restrict = fine NONE -> coarse INTERP(basisCtoF)^T */
+    OpField *i0 = &op->in[0], *o0 = &op->out[0];
+    const int prolong = qf->in[0].emode == CEED_EVAL_INTERP && qf->out[0].emode == CEED_EVAL_NONE;
+    const int restr = qf->in[0].emode == CEED_EVAL_NONE && qf->out[0].emode == CEED_EVAL_INTERP;
+    if ((prolong || restr) && i0->v == CEED_VECTOR_ACTIVE && o0->v == CEED_VECTOR_ACTIVE) {
+      OpField *c = prolong ? i0 : o0, *f = prolong ? o0 : i0;
+      static const int pairs[][2] = {{2, 3}, {3, 4}, {4, 5}, {3, 5}, {2, 4}, {2, 5}};
+      if (is_tensor3(c->b) && c->r && f->r && c->r != CEED_ELEMRESTRICTION_NONE && f->r != CEED_ELEMRESTRICTION_NONE &&
+          c->r->strided == 0 && f->r->strided == 0 && c->r->ncomp == 3 && f->r->ncomp == 3 && c->r->compstride == 1 &&
+          f->r->compstride == 1 && c->r->nelem == f->r->nelem && c->b->ncomp == 3 &&
+          c->r->elemsize == c->b->P * c->b->P * c->b->P && f->r->elemsize == c->b->Q * c->b->Q * c->b->Q)
+        for (size_t k = 0; k < sizeof pairs / sizeof pairs[0]; k++)
+          if (pairs[k][0] == c->b->P && pairs[k][1] == c->b->Q) op->kind = OP_FUSED_TRANSFER;
+    }
+  }
+  return 0;
+}
+
+int CeedOperatorIsFusedB200(CeedOperator op, int *isFused) {
+  if (op->composite) { *isFused = 0; return 0; }
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  *isFused = op->kind != OP_GENERIC;
+  return 0;
+}
+
+static int qf_physics(CeedQFunction qf, b200_physics *phys) {
+  if (!qf->ctx) return CeedError(qf->ceed, 1, "QFunction %s needs a Physics context (CeedQFunctionSetContext)", qf->name);
+  memcpy(phys, qf->ctx, sizeof *phys); /* {nu, E}: read through the host pointer, whatever ctxsize says */
+  return 0;
+}
+
+/* Jacobian cache for (qdata[, gradu]) -- rebuilt when either vector changed */
+static int jcache_get(CeedOperator op, const double **jc) {
+  Ceed ceed = op->ceed;
+  const int prob = op->problem;
+  CeedVector qd = op->in[1].v, gu = prob == B200_PROB_LINELAS ? NULL : op->in[2].v;
+  const int nelem = op->in[0].r->nelem, Q = op->in[0].b->Q;
+  JCacheEntry *e = ceed->jcaches;
+  while (e && !(e->qdata == qd && e->gradu == gu && e->problem == prob)) e = e->next;
+  if (!e) {
+    e = (JCacheEntry *)calloc(1, sizeof *e);
+    if (!e) return CeedError(ceed, 3, "out of memory");
+    e->qdata = qd; e->gradu = gu; e->problem = prob; e->nelem = nelem; e->Q = Q;
+    e->vq = e->vg = (uint64_t)-1;
+    const size_t bytes = sizeof(double) * (size_t)b200_jcache_ncomp(prob) * nelem * Q * Q * Q;
+    int rc = b200_malloc((void **)&e->d, bytes);
+    if (rc) { free(e); return CeedError(ceed, rc, "Jacobian cache allocation (%zu bytes): %s", bytes, b200_last_error()); }
+    e->next = ceed->jcaches;
+    ceed->jcaches = e;
+  }
+  if (e->vq != qd->version || (gu && e->vg != gu->version)) {
+    const double *q, *g = NULL;
+    CeedChk(vec_dev_read(qd, &q));
+    if (gu) CeedChk(vec_dev_read(gu, &g));
+    B2(ceed, b200_jcache_build(prob, nelem, Q, q, g, e->d));
+    e->vq = qd->version;
+    if (gu) e->vg = gu->version;
+  }
+  *jc = e->d;
+  return 0;
+}
+
+static int grow(Ceed ceed, double **buf, size_t *have, size_t need) {
+  if (*have >= need) return 0;
+  if (*buf) { B2(ceed, b200_sync()); B2(ceed, b200_free(*buf)); *buf = NULL; *have = 0; }
+  B2(ceed, b200_malloc((void **)buf, need));
+  *have = need;
+  return 0;
+}
+
+static int op_apply_generic(CeedOperator op, CeedVector in, CeedVector out) {
+  Ceed ceed = op->ceed;
+  CeedQFunction qf = op->qf;
+  CeedInt nelem = 0, nq = 0;
+  for (int i = 0; i < qf->nin + qf->nout; i++) {
+    OpField *f = i < qf->nin ? &op->in[i] : &op->out[i - qf->nin];
+    const CeedEvalMode em = i < qf->nin ? qf->in[i].emode : qf->out[i - qf->nin].emode;
+    if (f->r && f->r != CEED_ELEMRESTRICTION_NONE) {
+      if (nelem && nelem != f->r->nelem) return CeedError(ceed, 1, "operator fields disagree on the number of elements");
+      nelem = f->r->nelem;
+    }
+    if (em != CEED_EVAL_NONE && is_tensor3(f->b)) nq = f->b->Q * f->b->Q * f->b->Q;
+  }
+  if (!nq)
+    for (int i = 0; i < qf->nin && !nq; i++)
+      if (op->in[i].r && op->in[i].r != CEED_ELEMRESTRICTION_NONE) nq = op->in[i].r->elemsize;
+  if (!nelem || !nq) return CeedError(ceed, 1, "operator %s: cannot determine element / quadrature counts", qf->name);
+
+  const double *qin[MAXF];
+  double *qout[MAXF];
+  for (int i = 0; i < qf->nin; i++) {
+    OpField *f = &op->in[i];
+    const CeedEvalMode em = qf->in[i].emode;
+    const size_t qsz = sizeof(double) * (size_t)nelem * qf->in[i].size * nq;
+    if (em == CEED_EVAL_WEIGHT) {
+      if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_WEIGHT needs a basis", qf->in[i].name);
+      CeedChk(grow(ceed, &op->qbuf[i], &op->qbytes[i], qsz));
+      CeedChk(basis_apply_raw(f->b, nelem, 0, CEED_EVAL_WEIGHT, NULL, op->qbuf[i]));
+      qin[i] = op->qbuf[i];
+      continue;
+    }
+    CeedVector src = f->v == CEED_VECTOR_ACTIVE ? in : f->v;
+    if (!src || src == CEED_VECTOR_NONE) return CeedError(ceed, 1, "field \"%s\" has no input vector", qf->in[i].name);
+    if (!f->r || f->r == CEED_ELEMRESTRICTION_NONE) return CeedError(ceed, 1, "field \"%s\" needs an element restriction", qf->in[i].name);
+    const double *l;
+    CeedChk(vec_dev_read(src, &l));
+    const size_t esz = sizeof(double) * (size_t)nelem * f->r->ncomp * f->r->elemsize;
+    CeedChk(grow(ceed, &op->ebuf[i], &op->ebytes[i], esz));
+    CeedChk(rstr_apply_raw(f->r, 0, l, op->ebuf[i]));
+    if (em == CEED_EVAL_NONE) {
+      if (f->r->elemsize != nq || f->r->ncomp != qf->in[i].size)
+        return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_NONE size mismatch", qf->in[i].name);
+      qin[i] = op->ebuf[i];
+    } else {
+      if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": eval mode needs a tensor basis", qf->in[i].name);
+      if (qf->in[i].size != f->b->ncomp * (em == CEED_EVAL_GRAD ? 3 : 1))
+        return CeedError(ceed, 1, "field \"%s\": QFunction size %d does not match basis", qf->in[i].name, qf->in[i].size);
+      CeedChk(grow(ceed, &op->qbuf[i], &op->qbytes[i], qsz));
+      CeedChk(basis_apply_raw(f->b, nelem, 0, em, op->ebuf[i], op->qbuf[i]));
+      qin[i] = op->qbuf[i];
+    }
+  }
+  for (int i = 0; i < qf->nout; i++) {
+    const size_t qsz = sizeof(double) * (size_t)nelem * qf->out[i].size * nq;
+    CeedChk(grow(ceed, &op->qbuf[MAXF + i], &op->qbytes[MAXF + i], qsz));
+    qout[i] = op->qbuf[MAXF + i];
+  }
+  b200_physics phys = {0.3, 1.0};
+  const int id = qf->qf_id;
+  if (id != B200_QF_SETUPGEO && id != B200_QF_IDENTITY) CeedChk(qf_physics(qf, &phys));
+  B2(ceed, b200_qfunction_apply(id, &phys, qf->identity_size, nelem, nq, qf->nin, qin, qf->nout, qout));
+  for (int i = 0; i < qf->nout; i++) {
+    OpField *f = &op->out[i];
+    const CeedEvalMode em = qf->out[i].emode;
+    CeedVector dst = f->v == CEED_VECTOR_ACTIVE ? out : f->v;
+    if (!dst || dst == CEED_VECTOR_NONE) return CeedError(ceed, 1, "field \"%s\" has no output vector", qf->out[i].name);
+    if (!f->r || f->r == CEED_ELEMRESTRICTION_NONE) return CeedError(ceed, 1, "field \"%s\" needs an element restriction", qf->out[i].name);
+    double *l;
+    CeedChk(vec_dev_rw(dst, &l));
+    const double *e = qout[i];
+    if (em != CEED_EVAL_NONE) {
+      if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": eval mode needs a tensor basis", qf->out[i].name);
+      const size_t esz = sizeof(double) * (size_t)nelem * f->r->ncomp * f->r->elemsize;
+      CeedChk(grow(ceed, &op->ebuf[MAXF + i], &op->ebytes[MAXF + i], esz));
+      CeedChk(basis_apply_raw(f->b, nelem, 1, em, qout[i], op->ebuf[MAXF + i]));
+      e = op->ebuf[MAXF + i];
+    } else if (f->r->elemsize != nq || f->r->ncomp != qf->out[i].size) {
+      return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_NONE size mismatch", qf->out[i].name);
+    }
+    CeedChk(rstr_apply_raw(f->r, 1, e, l));
+  }
+  return 0;
+}
+
+int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
+  (void)request;
+  Ceed ceed = op->ceed;
+  if (op->composite) {
+    for (int i = 0; i < op->nsubs; i++) CeedChk(CeedOperatorApplyAdd(op->subs[i], in, out, request));
+    return 0;
+  }
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  if (op->kind == OP_GENERIC) return op_apply_generic(op, in, out);
+  const double *x;
+  double *y;
+  if (op->kind == OP_FUSED_TRANSFER) {
+    const int prolong = op->qf->in[0].emode == CEED_EVAL_INTERP;
+    OpField *c = prolong ? &op->in[0] : &op->out[0], *f = prolong ? &op->out[0] : &op->in[0];
+    CeedChk(vec_dev_read(in, &x));
+    CeedChk(vec_dev_rw(out, &y));
+    B2(ceed, b200_apply_transfer(!prolong, c->r->nelem, c->b->P, c->b->Q, c->b->interp1d, c->r->d_offsets, f->r->d_offsets,
+                                 NULL, x, y));
+    return 0;
+  }
+  OpField *u = &op->in[0];
+  b200_physics phys;
+  CeedChk(qf_physics(op->qf, &phys));
+  const int nelem = u->r->nelem, P = u->b->P, Q = u->b->Q;
+  if (in->length < u->r->lsize || out->length < u->r->lsize)
+    return CeedError(ceed, 1, "operator %s: active vectors shorter than the restriction's L-vector size %d", op->qf->name, u->r->lsize);
+  if (op->kind == OP_FUSED_JACOBIAN) {
+    const double *jc;
+    CeedChk(jcache_get(op, &jc));
+    CeedChk(vec_dev_read(in, &x));
+    CeedChk(vec_dev_rw(out, &y));
+    B2(ceed, b200_apply_jacobian(op->problem, &phys, nelem, P, Q, u->b->interp1d, u->b->grad1d, u->r->d_offsets, jc, x, y));
+  } else {
+    const double *qd;
+    double *gu = NULL;
+    CeedChk(vec_dev_read(op->in[1].v, &qd));
+    if (op->problem != B200_PROB_LINELAS) CeedChk(vec_dev_write(op->out[1].v, &gu));
+    CeedChk(vec_dev_read(in, &x));
+    CeedChk(vec_dev_rw(out, &y));
+    B2(ceed, b200_apply_residual(op->problem, &phys, nelem, P, Q, u->b->interp1d, u->b->grad1d, u->r->d_offsets, qd, gu, x, y));
+  }
+  return 0;
+}
+
+/* libCEED interface semantics: zero every output (active and passive), then ApplyAdd */
+int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
+  if (op->composite) {
+    if (out && out != CEED_VECTOR_NONE) CeedChk(CeedVectorSetValue(out, 0.0));
+    for (int i = 0; i < op->nsubs; i++) CeedChk(CeedOperatorApplyAdd(op->subs[i], in, out, request));
+    return 0;
+  }
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  for (int i = 0; i < op->qf->nout; i++) {
+    CeedVector v = op->out[i].v == CEED_VECTOR_ACTIVE ? out : op->out[i].v;
+    if (!v || v == CEED_VECTOR_NONE) continue;
+    /* the fused residual kernel overwrites every entry of its passive output (gradu) itself */
+    if (op->kind == OP_FUSED_RESIDUAL && i == 1) continue;
+    CeedChk(CeedVectorSetValue(v, 0.0));
+  }
+  return CeedOperatorApplyAdd(op, in, out, request);
+}
+
+int CeedOperatorLinearAssembleAddDiagonal(CeedOperator op, CeedVector assembled, CeedRequest *request) {
+  (void)request;
+  Ceed ceed = op->ceed;
+  if (op->composite) {
+    for (int i = 0; i < op->nsubs; i++) CeedChk(CeedOperatorLinearAssembleAddDiagonal(op->subs[i], assembled, request));
+    return 0;
+  }
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  if (op->kind != OP_FUSED_JACOBIAN && !(op->kind == OP_FUSED_RESIDUAL && op->problem == B200_PROB_LINELAS))
+    return CeedError(ceed, 1, "%s: CeedOperatorLinearAssembleDiagonal is implemented for the Jacobian operators (QFunction %s is not one)",
+                     CEED_B200_RESOURCE, op->qf->name);
+  OpField *u = &op->in[0];
+  b200_physics phys;
+  CeedChk(qf_physics(op->qf, &phys));
+  const double *jc;
+  double *d;
+  CeedChk(jcache_get(op, &jc));
+  CeedChk(vec_dev_rw(assembled, &d));
+  B2(ceed, b200_apply_diagonal(op->problem, &phys, u->r->nelem, u->b->P, u->b->Q, u->b->interp1d, u->b->grad1d,
+                               u->r->d_offsets, jc, d));
+  return 0;
+}
+int CeedOperatorLinearAssembleDiagonal(CeedOperator op, CeedVector assembled, CeedRequest *request) {
+  CeedChk(CeedVectorSetValue(assembled, 0.0));
+  return CeedOperatorLinearAssembleAddDiagonal(op, assembled, request);
+}
+
+int CeedOperatorDestroy(CeedOperator *op) {
+  if (!op || !*op) return 0;
+  CeedOperator o = *op;
+  *op = NULL;
+  if (--o->refcount > 0) return 0;
+  if (o->composite) {
+    for (int i = 0; i < o->nsubs; i++) CeedOperatorDestroy(&o->subs[i]);
+  } else {
+    for (int i = 0; i < 2 * MAXF; i++) {
+      OpField *f = i < MAXF ? &o->in[i] : &o->out[i - MAXF];
+      if (f->set) {
+        CeedElemRestriction r = f->r; CeedBasis b = f->b; CeedVector v = f->v;
+        if (r && r != CEED_ELEMRESTRICTION_NONE) CeedElemRestrictionDestroy(&r);
+        if (b && b != CEED_BASIS_COLLOCATED) CeedBasisDestroy(&b);
+        if (v && v != CEED_VECTOR_ACTIVE && v != CEED_VECTOR_NONE) CeedVectorDestroy(&v);
+      }
+      b200_free(o->ebuf[i]);
+      b200_free(o->qbuf[i]);
+    }
+    CeedQFunctionDestroy(&o->qf);
+  }
+  Ceed c = o->ceed;
+  free(o);
+  return CeedDestroy(&c);
+}

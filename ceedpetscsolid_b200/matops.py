@@ -1,0 +1,220 @@
+"""MatShell callbacks of the mini-app on the `/gpu/b200` backend.
+
+Mirrors /root/reference/src/matops.c function for function:
+  ApplyLocalCeedOp :26-60, FormResidual_Ceed :63-79, ApplyJacobianCoarse_Ceed :82-95,
+  ApplyJacobian_Ceed :98-112, Prolong_Ceed :115-157, Restrict_Ceed :160-203, GetDiag_Ceed :206-244
+and the context structs UserMult (/root/reference/elasticity.h:173-189, src/misc.c:26-70) and
+UserMultProlongRestr (elasticity.h:202-215, src/misc.c:73-146).
+
+PETSc is not available here; `LevelDM` stands in for the DM of one multigrid level: it owns
+the local (L-vector: owned + ghost + Dirichlet dofs, interlaced [node][3]) and global (owned,
+unconstrained dofs) layouts and performs DMGlobalToLocal / DMLocalToGlobal.  PETSc Vecs are
+torch float64 tensors (device tensors for `-memtype device`, host tensors for `-memtype host`).
+All device arithmetic is done by libceed_b200.so kernels.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ceed as libceed
+from .ceed import MEM_DEVICE, MEM_HOST, USE_POINTER, b2, lib
+
+
+class LevelDM:
+    """DM stand-in for one level (degree p) of a (brick of a) box mesh.
+
+    bc_faces: "all" (the `-test` marker label, setupdm.c:160-170), an iterable of (axis, side)
+    or None.  `halo`: a ceedpetscsolid_b200.halo.Halo for partitioned runs, else None.
+    """
+
+    def __init__(self, mesh, degree, bc_faces="all", halo=None, device="cuda", node_perm=None):
+        self.mesh, self.degree, self.halo = mesh, degree, halo
+        self.device = torch.device(device)
+        nn = mesh.num_nodes(degree)
+        self.lsize = 3 * nn
+        bc_nodes = mesh.boundary_mask(degree, bc_faces) if bc_faces is not None else np.zeros(nn, bool)
+        owned_nodes = halo.owned_node_mask if halo is not None else np.ones(nn, bool)
+        free_owned = (~bc_nodes) & owned_nodes
+        if node_perm is not None:  # local numbering is a permutation of the lexicographic one
+            fo = np.zeros(nn, bool); fo[node_perm] = free_owned
+            bc = np.zeros(nn, bool); bc[node_perm] = bc_nodes
+            free_owned, bc_nodes = fo, bc
+        self.bc_nodes = bc_nodes
+        fo_idx = np.flatnonzero(np.repeat(free_owned, 3)).astype(np.int32)
+        bc_idx = np.flatnonzero(np.repeat(bc_nodes, 3)).astype(np.int32)
+        self.nglobal = fo_idx.size
+        self.free_owned_idx = torch.from_numpy(fo_idx).to(self.device)
+        self.bc_idx = torch.from_numpy(bc_idx).to(self.device)
+        self._fo_host, self._bc_host = fo_idx, bc_idx
+
+    # ---- Vec creation (DMCreateGlobalVector / DMCreateLocalVector)
+    def create_global_vector(self, mem=MEM_DEVICE):
+        return torch.zeros(self.nglobal, dtype=torch.float64,
+                           device=self.device if mem == MEM_DEVICE else "cpu",
+                           pin_memory=(mem == MEM_HOST and torch.cuda.is_available()))
+
+    def create_local_vector(self, mem=MEM_DEVICE):
+        return torch.zeros(self.lsize, dtype=torch.float64,
+                           device=self.device if mem == MEM_DEVICE else "cpu",
+                           pin_memory=(mem == MEM_HOST and torch.cuda.is_available()))
+
+    # ---- DMGlobalToLocal(INSERT_VALUES) / DMLocalToGlobal(ADD_VALUES) (matops.c:33,57)
+    def global_to_local(self, X, Xloc):
+        if Xloc.is_cuda:
+            b2(lib.b200_scatter_set(Xloc.data_ptr(), self.free_owned_idx.data_ptr(), X.data_ptr(), self.nglobal))
+        else:
+            Xloc.numpy()[self._fo_host] = X.numpy()
+        if self.halo is not None:
+            self.halo.owner_to_ghost(Xloc)
+
+    def local_to_global(self, Yloc, Y):
+        """VecZeroEntries(Y); DMLocalToGlobal(dm, Yloc, ADD_VALUES, Y): constrained dofs dropped."""
+        if self.halo is not None:
+            self.halo.ghost_to_owner_add(Yloc)
+        if Yloc.is_cuda:
+            b2(lib.b200_gather(Y.data_ptr(), Yloc.data_ptr(), self.free_owned_idx.data_ptr(), self.nglobal))
+        else:
+            Y.numpy()[:] = Yloc.numpy()[self._fo_host]
+
+    def insert_boundary_values(self, Xloc, values):
+        """DMPlexInsertBoundaryValues stand-in: values = tensor over bc dofs (or None = zero)."""
+        if values is None:
+            return
+        if Xloc.is_cuda:
+            b2(lib.b200_scatter_set(Xloc.data_ptr(), self.bc_idx.data_ptr(), values.data_ptr(), self.bc_idx.numel()))
+        else:
+            Xloc.numpy()[self._bc_host] = values.cpu().numpy()
+
+
+@dataclass
+class UserMult:
+    """elasticity.h:173-189; wired by SetupJacobianCtx (src/misc.c:26-70)."""
+    dm: LevelDM
+    Xloc: torch.Tensor
+    Yloc: torch.Tensor
+    Xceed: object
+    Yceed: object
+    op: object
+    qf: object
+    ceed: object
+    phys: object = None
+    physSmoother: object = None
+    memType: int = MEM_DEVICE
+    loadIncrement: float = 1.0
+    bc_values: object = None  # callable(loadIncrement) -> tensor over dm.bc_idx, or None
+
+
+def setup_jacobian_ctx(dm, ceed, data, phys, physSmoother=None, memType=MEM_DEVICE):
+    """SetupJacobianCtx (src/misc.c:26-70)."""
+    return UserMult(dm=dm, Xloc=dm.create_local_vector(memType), Yloc=dm.create_local_vector(memType),
+                    Xceed=data.xceed, Yceed=data.yceed, op=data.opJacob, qf=data.qfJacob, ceed=ceed, phys=phys,
+                    physSmoother=physSmoother, memType=memType)
+
+
+def ApplyLocalCeedOp(X, Y, user):
+    """matops.c:26-60: Y = P^T A_loc P X."""
+    user.dm.global_to_local(X, user.Xloc)                         # :33
+    user.Yloc.zero_()                                             # :34
+    user.Xceed.set_array(user.Xloc, user.memType, USE_POINTER)    # :40
+    user.Yceed.set_array(user.Yloc, user.memType, USE_POINTER)    # :41
+    user.op.apply(user.Xceed, user.Yceed)                         # :46
+    user.Xceed.take_array(user.memType)                           # :49
+    user.Yceed.take_array(user.memType)                           # :50
+    user.dm.local_to_global(user.Yloc, Y)                         # :56-57
+
+
+def FormResidual_Ceed(X, Y, user):
+    """matops.c:63-79: boundary values at `loadIncrement`, then the residual operator
+    (which also rewrites gradu for the following Jacobian applies)."""
+    user.Xloc.zero_()
+    if user.bc_values is not None:
+        user.dm.insert_boundary_values(user.Xloc, user.bc_values(user.loadIncrement))
+    ApplyLocalCeedOp(X, Y, user)
+
+
+def ApplyJacobian_Ceed(user, X, Y):
+    """matops.c:98-112 (and ApplyJacobianCoarse_Ceed :82-95): zero boundary values, apply."""
+    user.Xloc.zero_()
+    ApplyLocalCeedOp(X, Y, user)
+
+
+def GetDiag_Ceed(user, D):
+    """matops.c:206-244."""
+    if user.physSmoother is not None:
+        user.qf.set_context(user.physSmoother)
+    user.Xceed.set_array(user.Xloc, user.memType, USE_POINTER)
+    user.op.linear_assemble_diagonal(user.Xceed)
+    if user.physSmoother is not None:
+        user.qf.set_context(user.phys)
+    user.Xceed.take_array(user.memType)
+    user.dm.local_to_global(user.Xloc, D)
+    user.Xloc.zero_()
+
+
+@dataclass
+class UserMultProlongRestr:
+    """elasticity.h:202-215; SetupProlongRestrictCtx (src/misc.c:73-146)."""
+    dmC: LevelDM
+    dmF: LevelDM
+    locVecC: torch.Tensor
+    locVecF: torch.Tensor
+    multVec: torch.Tensor
+    ceedVecC: object
+    ceedVecF: object
+    opProlong: object
+    opRestrict: object
+    ceed: object
+    memType: int = MEM_DEVICE
+
+
+def setup_prolong_restrict_ctx(dmC, dmF, ceed, dataC, dataF, userC, userF, memType=MEM_DEVICE):
+    """src/misc.c:73-146: shares the level work vectors; multVec = 1 / multiplicity of the fine
+    restriction, summed over ranks (L2G then G2L) before the reciprocal (:115-143)."""
+    mult_ceed = dataF.Erestrictu.create_vector()
+    dataF.Erestrictu.get_multiplicity(mult_ceed)
+    mult = torch.from_numpy(mult_ceed.to_numpy())
+    mult_ceed.destroy()
+    mult = mult.to(dmF.device) if memType == MEM_DEVICE else mult
+    if dmF.halo is not None:
+        dmF.halo.ghost_to_owner_add(mult)
+        dmF.halo.owner_to_ghost(mult)
+    multVec = torch.where(mult > 0, 1.0 / mult, mult)
+    return UserMultProlongRestr(dmC=dmC, dmF=dmF, locVecC=userC.Xloc, locVecF=userF.Xloc, multVec=multVec,
+                                ceedVecC=dataC.xceed, ceedVecF=dataF.xceed, opProlong=dataF.opProlong,
+                                opRestrict=dataF.opRestrict, ceed=ceed, memType=memType)
+
+
+def _pointwise_mult(w, x, y):
+    if w.is_cuda:
+        b2(lib.b200_vec_pointwise_mult(w.data_ptr(), x.data_ptr(), y.data_ptr(), w.numel()))
+    else:
+        torch.mul(x, y, out=w)
+
+
+def Prolong_Ceed(user, X, Y):
+    """matops.c:115-157."""
+    user.locVecC.zero_()
+    user.dmC.global_to_local(X, user.locVecC)
+    user.locVecF.zero_()
+    user.ceedVecC.set_array(user.locVecC, user.memType, USE_POINTER)
+    user.ceedVecF.set_array(user.locVecF, user.memType, USE_POINTER)
+    user.opProlong.apply(user.ceedVecC, user.ceedVecF)
+    user.ceedVecC.take_array(user.memType)
+    user.ceedVecF.take_array(user.memType)
+    _pointwise_mult(user.locVecF, user.locVecF, user.multVec)     # :149
+    user.dmF.local_to_global(user.locVecF, Y)
+
+
+def Restrict_Ceed(user, X, Y):
+    """matops.c:160-203."""
+    user.locVecF.zero_()
+    user.dmF.global_to_local(X, user.locVecF)
+    user.locVecC.zero_()
+    _pointwise_mult(user.locVecF, user.locVecF, user.multVec)     # :176
+    user.ceedVecF.set_array(user.locVecF, user.memType, USE_POINTER)
+    user.ceedVecC.set_array(user.locVecC, user.memType, USE_POINTER)
+    user.opRestrict.apply(user.ceedVecF, user.ceedVecC)
+    user.ceedVecF.take_array(user.memType)
+    user.ceedVecC.take_array(user.memType)
+    user.dmC.local_to_global(user.locVecC, Y)

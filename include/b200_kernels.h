@@ -1,0 +1,160 @@
+/* b200_kernels.h -- thin C-ABI over the hand-written sm_100a CUDA kernels of the
+ * `/gpu/b200` libCEED backend.  Plain pointers and sizes only (no CUDA, torch or C++
+ * types), so the backend proper (csrc/ceed_b200.c) is C99 and any host language can
+ * bind these entry points directly.
+ *
+ * Every function returns 0 on success or a CUDA error code (!= 0); b200_last_error()
+ * gives the message.  All device work is issued on the stream set with
+ * b200_set_stream() (default: the legacy default stream 0, which orders against PETSc
+ * VecCUDA kernels as SURVEY.md 8(b) "Threading / streams" requires).
+ *
+ * Each group cites the reference interface it replaces; libCEED itself is not vendored
+ * in the reference, its call sites are.
+ */
+#ifndef B200_KERNELS_H
+#define B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- problem / QFunction identifiers --------------------------------------------- */
+/* problemOptions[] /root/reference/src/setuplibceed.c:41-107 */
+enum { B200_PROB_LINELAS = 0, B200_PROB_HYPERSS = 1, B200_PROB_HYPERFS = 2 };
+
+/* user QFunctions recognised by name (the "<file>:<Name>" locator given to
+ * CeedQFunctionCreateInterior, setuplibceed.c:370,518,818) + the gallery Identity
+ * (elasticity.c:249-252) */
+enum {
+  B200_QF_NONE = 0,
+  B200_QF_SETUPGEO,    /* qfunctions/common.h:47  */
+  B200_QF_LINELAS_F,   /* qfunctions/linElas.h:39 */
+  B200_QF_LINELAS_DF,  /* qfunctions/linElas.h:163 */
+  B200_QF_HYPERSS_F,   /* qfunctions/hyperSS.h:60 */
+  B200_QF_HYPERSS_DF,  /* qfunctions/hyperSS.h:187 */
+  B200_QF_HYPERFS_F,   /* qfunctions/hyperFS.h:147 */
+  B200_QF_HYPERFS_DF,  /* qfunctions/hyperFS.h:286 */
+  B200_QF_IDENTITY     /* libCEED gallery "Identity" */
+};
+
+/* Physics_private {nu, E}  /root/reference/elasticity.h:30-37 */
+typedef struct { double nu, E; } b200_physics;
+
+/* ---- device / memory -------------------------------------------------------------- */
+int b200_device_count(int *count);
+int b200_set_device(int dev);
+int b200_get_device(int *dev);
+int b200_set_stream(void *cuda_stream);          /* cudaStream_t, NULL = legacy default */
+void *b200_get_stream(void);
+int b200_sync(void);                             /* synchronise the backend stream */
+const char *b200_last_error(void);
+int b200_device_name(char *buf, int len);
+int b200_sm_count(int *count);
+
+int b200_malloc(void **dptr, size_t bytes);
+int b200_free(void *dptr);
+int b200_malloc_host(void **hptr, size_t bytes); /* pinned */
+int b200_free_host(void *hptr);
+int b200_memset(void *dptr, int value, size_t bytes);
+int b200_memcpy_h2d(void *d, const void *h, size_t bytes);
+int b200_memcpy_d2h(void *h, const void *d, size_t bytes);   /* synchronises */
+int b200_memcpy_d2d(void *d, const void *s, size_t bytes);
+int b200_pointer_is_device(const void *p, int *is_device);
+
+/* launch counter: number of kernels of THIS library launched since the last reset */
+unsigned long long b200_launch_count(void);
+void b200_launch_count_reset(void);
+
+/* ---- CeedVector kernels (matops.c:34,56,149,176; misc.c:119-143) ------------------- */
+int b200_vec_set(double *d, double value, size_t n);
+int b200_vec_reciprocal(double *d, size_t n);
+int b200_vec_scale(double *d, double alpha, size_t n);
+int b200_vec_axpy(double *y, double alpha, const double *x, size_t n);            /* y += a x   */
+int b200_vec_aypx(double *y, double alpha, const double *x, size_t n);            /* y = x + a y */
+int b200_vec_axpby(double *z, double a, const double *x, double b, const double *y, size_t n);
+int b200_vec_pointwise_mult(double *w, const double *x, const double *y, size_t n);
+int b200_vec_dot(const double *x, const double *y, size_t n, double *dresult);    /* device scalar */
+int b200_vec_dot_host(const double *x, const double *y, size_t n, double *hresult);
+int b200_vec_norm_host(const double *x, size_t n, int norm_type, double *hresult); /* 0=1,1=2,2=max */
+/* index gather / scatter used by the halo exchange and the global<->local maps
+ * (DMGlobalToLocal / DMLocalToGlobal, matops.c:33,57) */
+int b200_gather(double *dst, const double *src, const int *idx, size_t n);        /* dst[i]=src[idx[i]] */
+int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n);   /* dst[idx[i]]=src[i] */
+int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n);   /* dst[idx[i]]+=src[i] */
+int b200_mask_zero(double *d, const int *idx, size_t n);                          /* d[idx[i]] = 0 */
+
+/* ---- layout of CEED_STRIDES_BACKEND vectors (setuplibceed.c:304-318) --------------- */
+/* The backend owns this layout.  For elemsize = Q^3 (2 <= Q <= 8) it is "q-blocked":
+ * elements in groups of EB = b200_elems_per_block(Q); inside group g holding ebn
+ * elements (ebn = EB except in the tail group):
+ *   index(e,c,q) = g*EB*ncomp*Q^3 + (c*Q + q%Q)*(ebn*Q^2) + (e%EB)*Q^2 + q/Q
+ * i.e. [group][comp][qx][elem-in-group][qy + Q*qz]; otherwise plain [elem][comp][node]. */
+int b200_elems_per_block(int Q);
+int b200_strided_layout_q(int elemsize);  /* returns Q if the blocked layout applies, else 0 */
+
+/* ---- generic path: CeedElemRestrictionApply (App. B.1) ----------------------------- */
+/* offsets restriction: E[e][c][n] <-> L[offsets[e*elemsize+n] + c*compstride] */
+int b200_restrict_offsets(int transpose, int nelem, int elemsize, int ncomp, int compstride,
+                          const int *d_offsets, const double *d_in, double *d_out);
+/* strided restriction; layout_q > 0 selects the q-blocked backend layout, else the three
+ * strides {node, comp, elem} are used */
+int b200_restrict_strided(int transpose, int nelem, int elemsize, int ncomp, int layout_q,
+                          long long s_node, long long s_comp, long long s_elem,
+                          const double *d_in, double *d_out);
+
+/* ---- generic path: CeedBasisApply for tensor H1 bases, dim = 3 (App. B.3) ---------- */
+/* emode: 1 INTERP, 2 GRAD, 4 WEIGHT.  E layout [elem][comp][P^3]; Q layouts
+ * INTERP [elem][comp][Q^3], GRAD [elem][dim][comp][Q^3], WEIGHT [elem][Q^3].
+ * d_interp1d/d_grad1d: device [Q*P]; d_qweight1d: device [Q]. */
+int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double *d_interp1d,
+                     const double *d_grad1d, const double *d_qweight1d, int transpose, int emode,
+                     const double *d_u, double *d_v);
+
+/* ---- generic path: CeedQFunctionApply for recognised QFunctions (App. B.4) ---------- */
+/* in[k] / out[k]: device Q-vectors [elem][size_k][nq] in field declaration order */
+int b200_qfunction_apply(int qf_id, const b200_physics *phys, int identity_size, int nelem, int nq,
+                         int nin, const double *const *d_in, int nout, double *const *d_out);
+
+/* ---- hot path: fused CeedOperatorApply (matops.c:46; setuplibceed.c:518-542,818-839) */
+/* y_L += E^T G^T D G E x_L in ONE kernel: offsets gather, sum-factorised gradient
+ * (interpolate + collocated derivative), QFunction, transposed gradient, scatter-add.
+ *   interp1d, grad1d : HOST [Q*P] basis matrices (CeedBasisCreateTensorH1Lagrange)
+ *   qdata            : device, backend strided layout, 10 comps
+ *   gradu            : device, backend strided layout, 9 comps (written; NULL for linElas)
+ * Supported: 2 <= P <= Q <= 8 (P, Q as instantiated; see b200_fused_supported). */
+int b200_fused_supported(int P, int Q);
+int b200_apply_residual(int problem, const b200_physics *phys, int nelem, int P, int Q,
+                        const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
+                        const double *d_qdata, double *d_gradu, const double *d_x, double *d_y);
+
+/* Jacobian cache ("jcache"): per quadrature point, everything the Jacobian action needs
+ * in its cheapest algebraic form, built from (qdata, gradu) once per linearisation point
+ * and shared by all p-multigrid levels (they share the fine quadrature data,
+ * setuplibceed.c:757,833-839).  Components per problem: b200_jcache_ncomp(). */
+int b200_jcache_ncomp(int problem);
+int b200_jcache_build(int problem, int nelem, int Q, const double *d_qdata, const double *d_gradu,
+                      double *d_jcache);
+int b200_apply_jacobian(int problem, const b200_physics *phys, int nelem, int P, int Q,
+                        const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
+                        const double *d_jcache, const double *d_x, double *d_y);
+
+/* CeedOperatorLinearAssembleDiagonal (matops.c:227; App. B.5): diag_L += E^T diag_e */
+int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P, int Q,
+                        const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
+                        const double *d_jcache, double *d_diag);
+
+/* p-multigrid transfer (matops.c:115-203): out_L += Eo^T I^(T) Ei in_L, identity QFunction,
+ * interpolation Pc -> Pf at the fine GLL points; transpose = 1 is the restriction.
+ * d_mult (may be NULL): fine-level inverse multiplicity applied to the fine vector
+ * (after prolongation / before restriction, matops.c:149,176). */
+int b200_apply_transfer(int transpose, int nelem, int Pc, int Pf, const double *h_interpCtoF,
+                        const int *d_offc, const int *d_offf, const double *d_mult,
+                        const double *d_in, double *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_KERNELS_H */

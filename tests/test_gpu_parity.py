@@ -1,0 +1,147 @@
+"""Parity of the /gpu/b200 CUDA path against the CPU oracle, through the libCEED C API
+(libceed_b200.so).  FP64; tolerance from BASELINE.json north_star: 1e-12 relative."""
+import numpy as np
+import pytest
+
+from helpers import OracleProblem, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_helpers
+    return gpu_helpers
+
+
+CASES = [  # problem, n, p, qextra, perm
+    ("linElas", 3, 1, 0, None), ("linElas", 4, 2, 0, None), ("linElas", 3, 3, 0, 11),
+    ("hyperSS", 3, 2, 0, None), ("hyperSS", 4, 3, 0, None), ("hyperSS", 2, 4, 0, 12),
+    ("hyperFS", 3, 2, 0, None), ("hyperFS", 3, 3, 0, None), ("hyperFS", 3, 4, 0, None),
+    ("hyperFS", 2, 4, 1, None), ("hyperFS", 2, 2, 1, 13), ("hyperFS", (7, 2, 3), 4, 0, None),
+]
+
+
+@pytest.mark.parametrize("problem,n,p,qextra,perm", CASES)
+def test_setupgeo_residual_jacobian_diagonal(G, problem, n, p, qextra, perm):
+    g = G.GpuProblem(problem, n, p, qextra=qextra, node_perm_seed=perm)
+    o = OracleProblem(problem, n, p, qextra=qextra)
+    # geometric factors (generic path: restriction + basis + SetupGeo kernels)
+    qd = g.strided_to_plain(g.fine.Erestrictqdi, g.fine.qdata)
+    assert rel_err(qd, o.qdata) < TOL
+    # residual (fused) and the gradu it stores
+    yo = o.residual_fine(o.u_fine)
+    yg = g.residual()
+    if perm is not None:
+        tmp = np.empty_like(yo).reshape(-1, 3); tmp[g.perm] = yo.reshape(-1, 3); yo = tmp.reshape(-1)
+    assert g.fine.opApply.is_fused
+    assert rel_err(yg, yo) < TOL
+    if o.has_gradu:
+        gu = g.strided_to_plain(g.fine.ErestrictGradui, g.fine.gradu)
+        assert rel_err(gu, o.gradu) < TOL
+    # Jacobian on every p-multigrid level (all levels stream the fine quadrature data)
+    rng = np.random.default_rng(1)
+    for level, deg in enumerate(g.degrees):
+        ol = OracleProblem(problem, n, p, pl=deg, qextra=qextra)
+        x = rng.standard_normal(ol.lsize)
+        yo = ol.jacobian(x)
+        do = ol.diagonal()
+        xg = x
+        if perm is not None and level == len(g.degrees) - 1:
+            def P(v):
+                t = np.empty_like(v).reshape(-1, 3); t[g.perm] = v.reshape(-1, 3); return t.reshape(-1)
+            xg, yo, do = P(x), P(yo), P(do)
+        assert g.data[level].opJacob.is_fused
+        assert rel_err(g.jacobian(level, xg), yo) < TOL, (level, deg)
+        assert rel_err(g.diagonal(level), do) < TOL, (level, deg)
+
+
+def test_jacobian_tracks_new_linearisation_point(G):
+    """gradu rewritten by a residual evaluation invalidates the Jacobian cache."""
+    g = G.GpuProblem("hyperFS", 3, 2)
+    o = OracleProblem("hyperFS", 3, 2)
+    x = np.random.default_rng(2).standard_normal(o.lsize)
+    g.residual()
+    y1 = g.jacobian(len(g.degrees) - 1, x)
+    u2 = 1.7 * o.u_fine
+    o.residual_fine(u2)
+    g.residual(u2)
+    y2 = g.jacobian(len(g.degrees) - 1, x)
+    assert rel_err(y2, o.jacobian(x)) < TOL
+    assert rel_err(y2, y1) > 1e-6
+
+
+def test_generic_path_operator_matches_fused(G):
+    """(P,Q) = (4,6) is not instantiated as a fused kernel -> restriction/basis/QFunction kernels."""
+    g = G.GpuProblem("hyperFS", 2, 3, qextra=2, multigrid="none")
+    o = OracleProblem("hyperFS", 2, 3, qextra=2)
+    assert not g.fine.opApply.is_fused and not g.data[-1].opJacob.is_fused
+    assert rel_err(g.residual(), o.residual_fine(o.u_fine)) < TOL
+    x = np.random.default_rng(3).standard_normal(o.lsize)
+    assert rel_err(g.jacobian(0, x), o.jacobian(x)) < TOL
+
+
+def test_transfer_operators_and_multiplicity(G):
+    from oracle import oracle
+    g = G.GpuProblem("hyperFS", 3, 4)
+    rng = np.random.default_rng(4)
+    for level in range(1, len(g.degrees)):
+        pc, pf = g.degrees[level - 1], g.degrees[level]
+        offc, offf = g.mesh.offsets(pc), g.mesh.offsets(pf)
+        lc, lf = g.mesh.lsize(pc), g.mesh.lsize(pf)
+        c, f = rng.standard_normal(lc), rng.standard_normal(lf)
+        d = g.data[level]
+        assert d.opProlong.is_fused and d.opRestrict.is_fused
+        assert rel_err(g.apply(d.opProlong, c, lf), oracle.transfer(False, g.mesh.nelem, pc + 1, pf + 1, offc, offf, c, lf)) < TOL
+        assert rel_err(g.apply(d.opRestrict, f, lc), oracle.transfer(True, g.mesh.nelem, pc + 1, pf + 1, offc, offf, f, lc)) < TOL
+        m = d.Erestrictu.create_vector()
+        d.Erestrictu.get_multiplicity(m)
+        np.testing.assert_array_equal(m.to_numpy(), oracle.multiplicity(g.mesh.nelem, (pf + 1) ** 3, 3, lf, offf))
+
+
+def test_matshell_callbacks_device_and_host_memtype(G):
+    """ApplyJacobian_Ceed / FormResidual_Ceed / GetDiag_Ceed through UserMult, both memtypes."""
+    import torch
+    from ceedpetscsolid_b200 import matops
+    from ceedpetscsolid_b200.ceed import MEM_DEVICE, MEM_HOST
+    g = G.GpuProblem("hyperFS", 3, 2)
+    o = OracleProblem("hyperFS", 3, 2)
+    g.residual()
+    lvl = len(g.degrees) - 1
+    dm = matops.LevelDM(g.mesh, g.degrees[lvl], bc_faces="all")
+    free = ~np.repeat(dm.bc_nodes, 3)
+    xg = np.random.default_rng(5).standard_normal(dm.nglobal)
+    xl = np.zeros(o.lsize); xl[free] = xg
+    yref = o.jacobian(xl)[free]
+    dref = o.diagonal()[free]
+    for mem in (MEM_DEVICE, MEM_HOST):
+        user = matops.setup_jacobian_ctx(dm, g.ceed, g.data[lvl], g.phys, memType=mem)
+        X = dm.create_global_vector(mem); Y = dm.create_global_vector(mem); D = dm.create_global_vector(mem)
+        X.copy_(torch.from_numpy(xg))
+        matops.ApplyJacobian_Ceed(user, X, Y)
+        matops.GetDiag_Ceed(user, D)
+        torch.cuda.synchronize()
+        assert rel_err(Y.cpu().numpy(), yref) < TOL
+        assert rel_err(D.cpu().numpy(), dref) < TOL
+        assert float(user.Xloc.abs().max()) == 0.0  # GetDiag_Ceed re-zeroes Xloc (matops.c:241)
+
+
+def test_errors_are_loud(G):
+    from ceedpetscsolid_b200 import ceed as libceed
+    c = libceed.Ceed("/gpu/b200")
+    with pytest.raises(libceed.CeedError):
+        libceed.Ceed("/cpu/self")
+    qf = c.QFunction(1, "somewhere/user.h:NotAKnownQFunction")
+    qf.add_input("u", 1, libceed.EVAL_NONE)
+    qf.add_output("v", 1, libceed.EVAL_NONE)
+    r = c.StridedElemRestriction(2, 8, 1, 16)
+    op = c.Operator(qf)
+    op.set_field("u", r, libceed.BASIS_COLLOCATED, libceed.VECTOR_ACTIVE)
+    op.set_field("v", r, libceed.BASIS_COLLOCATED, libceed.VECTOR_ACTIVE)
+    u, v = c.Vector(16), c.Vector(16)
+    u.set_value(1.0)
+    with pytest.raises(libceed.CeedError, match="no CPU fallback"):
+        op.apply(u, v)
+    with pytest.raises(libceed.CeedError):
+        c.ElemRestriction(1, 8, 3, 1, 10, np.arange(8) * 3)  # offsets out of range
