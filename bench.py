@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: GDoF/s of the hyperFS (finite-strain Neo-Hookean) Jacobian
+MatMult at p = 4 on a synthetic box mesh (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # /gpu/b200 arm
+    python bench.py --impl reference --gpus N ...            # CPU arm (restated /cpu/self)
+
+One "step" = one MatShell MatMult of the fine-level Jacobian: ApplyJacobian_Ceed
+(/root/reference/src/matops.c:98-112) = zero Dirichlet inputs, DMGlobalToLocal (+ halo),
+zero Yloc, CeedOperatorApply (ONE fused kernel), DMLocalToGlobal (+ halo).
+Workload at N = 1: BASELINE.json configs[2], box 64^3, degree 4 (262 144 elements,
+50.9 M DoFs).  N > 1: weak scaling, one 64^3 brick per GPU (2x1x1, 2x2x1, 2x2x2 bricks),
+NCCL halo exchange; `--scaling strong` shards the ~100 M-DoF 80^3 box of configs[3] instead.
+Inputs (4.5 GB of per-quadrature-point data per GPU) are far larger than L2, so no explicit
+L2 flush is needed between timed iterations.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+ALG_BYTES_PER_ELEM = {  # 8 Q^3 (10 + g) + 4 P^3 + 48 p^3
+    ("hyperFS", 4): 22572, ("hyperSS", 3): 11280, ("linElas", 2): 2652,
+}
+
+
+def alg_bytes(problem, p, qextra=0):
+    P, Q = p + 1, p + 1 + qextra
+    g = 0 if problem == "linElas" else 9
+    return 8 * Q ** 3 * (10 + g) + 4 * P ** 3 + 48 * p ** 3
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_leg(problem, p, n_cpu, steps, warmup):
+    """Times the CPU oracle (restated /cpu/self operator; the reference's own QFunctions when
+    oracle/_ref is built) on a bounded sample of the workload, all host threads."""
+    from helpers import OracleProblem
+    from oracle import oracle
+    pr = OracleProblem(problem, n_cpu, p, which=oracle.default_which())
+    x = np.random.default_rng(1).standard_normal(pr.lsize)
+    y = np.zeros_like(x)
+    for _ in range(max(1, warmup)):
+        pr_y = oracle.operator_apply(problem, True, (0.3, 1.0), pr.nelem, pr.P, pr.Q, pr.B, pr.D, pr.offsets,
+                                     pr.qdata, pr.gradu, x, oracle.default_which(), y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pr_y = oracle.operator_apply(problem, True, (0.3, 1.0), pr.nelem, pr.P, pr.Q, pr.B, pr.D, pr.offsets,
+                                     pr.qdata, pr.gradu, x, oracle.default_which(), y)
+    dt = (time.perf_counter() - t0) / steps
+    del pr_y
+    dofs = pr.lsize
+    return {"value": dofs / dt / 1e9, "unit": "GDoF/s", "cores": oracle.num_threads(),
+            "kind": "port",
+            "sample": f"{problem} p={p} Jacobian apply on a {n_cpu}^3 box ({pr.nelem} elements, {dofs} DoFs), "
+                      f"{steps} applies, restated /cpu/self operator (oracle/ceed_oracle.c, OpenMP over elements) calling "
+                      f"{'the reference QFunctions compiled from /root/reference (oracle/_ref)' if oracle.default_which() == 'ref' else 'the ported QFunctions (oracle/qf_port.c)'}",
+            "ms_per_apply": dt * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--problem", default="hyperFS")
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--n", type=int, default=64, help="elements per direction per GPU (weak) / of the whole box (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--n-cpu", type=int, default=16, help="box size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    problem, p = args.problem, args.degree
+    workload = (f"{problem} degree {p} Jacobian MatMult, box {args.n}^3 per GPU" if args.scaling == "weak"
+                else f"{problem} degree {p} Jacobian MatMult, box {args.n}^3 sharded")
+    config = {"workload": workload, "problem": problem, "degree": p, "levels": "fine level of {1,2,4}",
+              "elements_per_gpu": None, "scatter": "fp64 atomics", "l2": "inputs larger than L2 (no flush needed)",
+              "bricks": None}
+
+    # ------------------------------------------------------------------ CPU reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 20))
+        cb = cpu_leg(problem, p, args.n_cpu, steps, min(args.warmup, 2))
+        line = {"impl": "reference", "metric": "GDoF/s of hyperFS Jacobian MatMult at p=4", "value": cb["value"],
+                "unit": "GDoF/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+                "ms_per_step": cb["ms_per_apply"], "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ /gpu/b200 arm
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from ceedpetscsolid_b200 import ceed as libceed
+    from ceedpetscsolid_b200 import matops, setuplibceed
+    from ceedpetscsolid_b200.mesh import BoxMesh, grid_for, smooth_displacement
+
+    grid = grid_for(world)
+    if args.scaling == "weak":
+        gmesh = BoxMesh(n=(args.n * grid[0], args.n * grid[1], args.n * grid[2]), perturb=0.08, seed=0)
+    else:
+        gmesh = BoxMesh(n=(args.n,) * 3, perturb=0.08, seed=0)
+    mesh = gmesh.brick(grid, rank) if world > 1 else gmesh
+    config["elements_per_gpu"] = mesh.nelem
+    config["bricks"] = "x".join(map(str, grid))
+
+    ceed = libceed.Ceed(f"/gpu/b200:device_id={local_rank}")
+    degrees, data, phys = setuplibceed.setup_all(ceed, mesh, problem, p)
+    fine = len(degrees) - 1
+    halo = None
+    if world > 1:
+        from ceedpetscsolid_b200.halo import Halo
+        halo = Halo(gmesh, grid, rank, p, dist)
+    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo)
+    user = matops.setup_jacobian_ctx(dm, ceed, data[fine], phys)
+
+    # state: smooth admissible displacement -> residual fills gradu
+    u = torch.from_numpy(smooth_displacement(mesh.node_coords(p)).reshape(-1)).cuda()
+    uc, rc = ceed.Vector(u.numel()), ceed.Vector(u.numel())
+    r = torch.zeros_like(u)
+    uc.set_array(u); rc.set_array(r)
+    data[fine].opApply.apply(uc, rc)
+    uc.take_array(); rc.take_array()
+    del u, r
+    X, Y = dm.create_global_vector(), dm.create_global_vector()
+    X.copy_(torch.from_numpy(np.random.default_rng(1 + rank).standard_normal(dm.nglobal)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        matops.ApplyJacobian_Ceed(user, X, Y)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    libceed.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        matops.ApplyJacobian_Ceed(user, X, Y)
+    e1.record()
+    barrier()
+    launches = libceed.launch_count()
+    clocks = sampler.result()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    global_nodes = gmesh.num_nodes(p)
+    dofs = 3 * global_nodes
+    dofs_unconstrained = 3 * int(np.prod([gmesh.n[d] * p - 1 for d in range(3)]))
+    value = dofs * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- dominant kernel alone (fused Jacobian apply), CUDA events on the launching stream
+    xl, yl = dm.create_local_vector(), dm.create_local_vector()
+    xl.copy_(torch.from_numpy(np.random.default_rng(7).standard_normal(dm.lsize)))
+    xc, yc = data[fine].xceed, data[fine].yceed
+    xc.set_array(xl); yc.set_array(yl)
+    for _ in range(3):
+        data[fine].opJacob.apply_add(xc, yc)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nk = max(args.steps, 10)
+    k0.record()
+    for _ in range(nk):
+        data[fine].opJacob.apply_add(xc, yc)
+    k1.record()
+    torch.cuda.synchronize()
+    kms = k0.elapsed_time(k1) / nk
+    xc.take_array(); yc.take_array()
+    peak, peak_src = measured_peaks()
+    ab = alg_bytes(problem, p) * mesh.nelem
+    achieved = ab / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_fused_apply<P=5,Q=5,hyperFS,Jacobian>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": kms, "algorithmic_bytes_per_launch": ab,
+                "algorithmic_bytes_per_element": alg_bytes(problem, p),
+                "kernel_gdofs": 3 * mesh.num_nodes(p) / (kms * 1e-3) / 1e9}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            tj = json.load(f)
+        if tj.get("elements") == mesh.nelem:
+            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+
+    # ---- e2e: the libCEED boundary with HOST buffers (-memtype host): SetArray(HOST), Apply, TakeArray(HOST)
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(dm.lsize, dtype=torch.float64).pin_memory()
+        yh = torch.zeros(dm.lsize, dtype=torch.float64).pin_memory()
+        xh.copy_(xl.cpu())
+        nrep = max(3, min(args.steps, 10))
+        for it in range(2 + nrep):
+            if it == 2:
+                barrier()
+                t0 = time.perf_counter()
+            xc.set_array(xh, libceed.MEM_HOST)
+            yc.set_array(yh, libceed.MEM_HOST)
+            data[fine].opJacob.apply(xc, yc)
+            xc.take_array(libceed.MEM_HOST)
+            yc.take_array(libceed.MEM_HOST)
+        barrier()
+        dt = (time.perf_counter() - t0) / nrep
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": dofs / dt / 1e9, "unit": "GDoF/s", "h2d_bytes_per_step": int(dm.lsize * 8),
+               "d2h_bytes_per_step": int(dm.lsize * 8), "ms_per_step": dt * 1e3,
+               "what": "CeedVectorSetArray(HOST,USE_POINTER) + CeedOperatorApply + CeedVectorTakeArray(HOST) on pinned host L-vectors"}
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu:
+            cb = cpu_leg(problem, p, args.n_cpu, 5, 1)
+        line = {"metric": "GDoF/s of hyperFS Jacobian MatMult at p=4", "value": value, "unit": "GDoF/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "dofs": dofs, "dofs_unconstrained": dofs_unconstrained,
+                "value_unconstrained_dofs": dofs_unconstrained * args.steps / (ms * 1e-3) / 1e9,
+                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,17 +27,18 @@ int set_error_msg(const char *msg);
   } while (0)
 
 // elements per thread block of the fused kernels == group size of the q-blocked layout
-__host__ __device__ constexpr int elems_per_block(int Q) {
-  return Q <= 2 ? 32 : Q == 3 ? 14 : Q == 4 ? 8 : Q == 5 ? 5 : Q == 6 ? 3 : 2;
-}
+__host__ __device__ constexpr int elems_per_block(int Q) { return Q <= 3 ? 16 : 8; }
 
-// index of (element e, component c, point q) in a q-blocked backend-strided vector
+// Index of (element e, component c, point q) in a q-blocked backend-strided vector:
+// groups of EB elements; inside a group holding ebn elements (ebn = EB except in the tail)
+//   [comp][qx][t = qy + Q*qz][element-in-group]
+// so that the fused kernels' lane id (tid = t*ebn + e) walks contiguous memory.
 __host__ __device__ inline size_t qblocked_index(int nelem, int ncomp, int Q, int e, int c, int q) {
   const int EB = elems_per_block(Q), T = Q * Q, Q3 = Q * Q * Q;
   const int g = e / EB, ei = e - g * EB;
   const int rem = nelem - g * EB;
   const int ebn = rem < EB ? rem : EB;
-  return (size_t)g * EB * ncomp * Q3 + (size_t)(c * Q + q % Q) * (ebn * T) + (size_t)ei * T + q / Q;
+  return (size_t)g * EB * ncomp * Q3 + (size_t)(c * Q + q % Q) * (ebn * T) + (size_t)(q / Q) * ebn + ei;
 }
 
 // ---------------------------------------------------------------------------------

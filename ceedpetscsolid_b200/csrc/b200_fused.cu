@@ -36,30 +36,51 @@ template <int Q> struct Cfg {
   static constexpr int EB = elems_per_block(Q);
   static constexpr int NT = ((T * EB + 31) / 32) * 32;
   static constexpr int Q3 = Q * Q * Q;
-  static constexpr int SE = 9 * Q3 + ((9 * Q3) % 2 == 0 ? 1 : 2);  // odd element stride
+  // Shared-memory lattice with ODD strides (1, QP, QP^2) and lanes ordered element-fastest
+  // (tid = t*EB + e): a half-warp then holds EB=16 elements of one line, or 8 elements of two
+  // neighbouring lines whose offsets differ by an odd number; with the element stride SE odd
+  // (EB=16) or = 2 mod 16 (EB=8) every 64-bit shared access of every line orientation is
+  // bank-conflict free (checked exhaustively in tests/test_layout.py).
+  static constexpr int QP = (Q % 2) ? Q : Q + 1;
+  static constexpr int SY = QP, SZ = QP * QP, SC = QP * QP * QP;
+  static constexpr int SE0 = 9 * SC;
+  static constexpr int SE = EB == 8 ? SE0 + ((2 - SE0 % 16) + 16) % 16 : (SE0 | 1);
   static constexpr size_t SMEM = (size_t)EB * SE * sizeof(double);
 };
 
-#define IDX(c, x, y, z) ((c) * Q3 + ((z) * Q + (y)) * Q + (x))
+#define IDX(c, x, y, z) ((c) * SC + (z) * SZ + (y) * SY + (x))
+
+// one thread asks the L2 to fetch this CTA's whole slab of per-point data (contiguous in the
+// q-blocked layout) while the CTA is busy with the gather and the interpolation stages
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) {
+  bytes &= ~15u;
+  if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 enum { MODE_RESIDUAL = 0, MODE_JACOBIAN = 1 };
 
 template <int P, int Q, int PROB, int MODE>
-__global__ void __launch_bounds__(Cfg<Q>::NT)
+__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? 2 : 1)
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
+  constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
   constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
-  const int eb = tid / T, t = tid - eb * T, a = t % Q, b = t / Q;
+  const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
   const int blk = blockIdx.x;
   const int rem = nelem - blk * EB;
   const int ebn = rem < EB ? rem : EB;
-  const bool act = eb < ebn;
+  const bool act = t < T && eb < ebn;
   const int e = blk * EB + eb;
-  double *R0 = smem + eb * SE, *R1 = R0 + 3 * Q3, *R2 = R1 + 3 * Q3;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * SC, *R2 = R1 + 3 * SC;
+  // per-point data of this CTA: slab base, lane offset and plane stride (q-blocked layout)
+  const double *qslab = qa + (size_t)blk * EB * NC * Q3;
+  const size_t ebt = (size_t)ebn * T;
+  const int lane = t * ebn + eb;
+  if (tid == 0) l2_prefetch_bulk(qslab, (unsigned)(ebt * Q * NC * sizeof(double)));
 
   // ---- phase 0: gather node z-lines, contract z with B
   if (act && a < P && b < P) {
@@ -126,7 +147,10 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   }
   __syncthreads();
   // ---- phase 3: y-lines (a = qx, b = qz): d/dy -> R1;  phase 4: z-lines (a = qx, b = qy): d/dz -> R2
+  double qn[NC];  // per-point data of the NEXT quadrature point: loads stay in flight under the math
   if (act) {
+#pragma unroll
+    for (int n = 0; n < NC; n++) qn[n] = __ldcs(qslab + (size_t)(n * Q) * ebt + lane);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       double in[Q];
@@ -154,13 +178,15 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   // ---- phase 5: QFunction at the Q points of this x-line; phase 6: d/dx^T in registers
   if (act) {
     double Wx[3][Q];
-    const size_t gb = (size_t)blk * EB * NC * Q3 + tid;
-    const size_t ebt = (size_t)ebn * T;
 #pragma unroll
     for (int qx = 0; qx < Q; qx++) {
       double qd[NC], H[3][3], W[3][3];
 #pragma unroll
-      for (int n = 0; n < NC; n++) qd[n] = __ldcs(qa + gb + (size_t)(n * Q + qx) * ebt);
+      for (int n = 0; n < NC; n++) qd[n] = qn[n];
+      if (qx + 1 < Q) {
+#pragma unroll
+        for (int n = 0; n < NC; n++) qn[n] = __ldcs(qslab + (size_t)(n * Q + qx + 1) * ebt + lane);
+      }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         H[c][0] = Hx[c][qx];
@@ -180,11 +206,11 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
         } else {
           if (PROB == B200_PROB_HYPERSS) hyperss_f_point(mt, qd[0], A, H, g, W);
           else hyperfs_f_point(mt, qd[0], A, H, g, W);
-          const size_t gg = (size_t)blk * EB * 9 * Q3 + tid;
+          double *gslab = gradu + (size_t)blk * EB * 9 * Q3 + lane;
 #pragma unroll
           for (int c = 0; c < 3; c++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) __stcs(gradu + gg + (size_t)((c * 3 + k) * Q + qx) * ebt, g[c][k]);
+            for (int k = 0; k < 3; k++) __stcs(gslab + (size_t)((c * 3 + k) * Q + qx) * ebt, g[c][k]);
         }
       }
 #pragma unroll
@@ -263,12 +289,8 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
     }
   }
   __syncthreads();
-  // ---- phase 10: x-lines (a = j < P, b = k < P): B^T along x, scatter-add
+  // ---- phase 10: x-lines (a = j < P, b = k < P): B^T along x -> R0 (free since phase 8)
   if (act && a < P && b < P) {
-    const int *off = offsets + (size_t)e * P3 + (b * P + a) * P;
-    int o[P];
-#pragma unroll
-    for (int i = 0; i < P; i++) o[i] = __ldg(off + i);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       double in[Q];
@@ -279,8 +301,22 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
         double s = 0;
 #pragma unroll
         for (int qx = 0; qx < Q; qx++) s += m.B[qx * P + i] * in[qx];
-        atomicAdd(y + o[i] + c, s);
+        R0[IDX(c, i, a, b)] = s;
       }
+    }
+  }
+  __syncthreads();
+  // ---- scatter-add in L-vector order: consecutive lanes -> (node, component) pairs that are
+  // consecutive in memory for interlaced dofs, so one RED request touches few sectors
+  {
+    const int total = ebn * P3 * 3;
+    const int *offb = offsets + (size_t)blk * EB * P3;
+    for (int f = tid; f < total; f += Cfg<Q>::NT) {
+      const int el = f / (3 * P3), r = f - el * (3 * P3);
+      const int node = r / 3, c = r - node * 3;
+      const int i = node % P, j = (node / P) % P, k = node / (P * P);
+      const double v = smem[el * SE + IDX(c, i, j, k)];
+      atomicAdd(y + __ldg(offb + el * P3 + node) + c, v);
     }
   }
 }
@@ -334,17 +370,18 @@ __global__ void __launch_bounds__(Cfg<Q>::NT)
 k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ Material mt, int nelem,
              const int *__restrict__ offsets, const double *__restrict__ jcp, double *__restrict__ diag) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
+  constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
   constexpr int NC = JCache<PROB>::N;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
-  const int eb = tid / T, t = tid - eb * T, a = t % Q, b = t / Q;
+  const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
   const int blk = blockIdx.x;
   const int rem = nelem - blk * EB;
   const int ebn = rem < EB ? rem : EB;
-  const bool act = eb < ebn;
+  const bool act = t < T && eb < ebn;
   const int e = blk * EB + eb;
-  double *R0 = smem + eb * SE, *R1 = R0 + 3 * Q3;
-  const size_t gb = (size_t)blk * EB * NC * Q3 + tid;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * SC;
+  const size_t gb = (size_t)blk * EB * NC * Q3 + (size_t)(t * ebn + eb);
   const size_t ebt = (size_t)ebn * T;
 
   for (int c = 0; c < 3; c++) {
@@ -443,16 +480,17 @@ k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__r
            const int *__restrict__ offf, const double *__restrict__ mult, const double *__restrict__ in,
            double *__restrict__ out) {
   constexpr int Q = PF;  // lattice extent used for smem indexing
-  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE;
+  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, SE = Cfg<Q>::SE;
+  constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
   constexpr int NI = TR ? PF : PC, NO = TR ? PC : PF;  // line extents in / out
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
-  const int eb = tid / T, t = tid - eb * T, a = t % Q, b = t / Q;
+  const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
   const int rem = nelem - blockIdx.x * EB;
   const int ebn = rem < EB ? rem : EB;
-  const bool act = eb < ebn;
+  const bool act = t < T && eb < ebn;
   const int e = blockIdx.x * EB + eb;
-  double *R0 = smem + eb * SE, *R1 = R0 + 3 * Q3;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * SC;
   const int *oin = (TR ? offf : offc) + (size_t)e * NI * NI * NI;
   const int *oout = (TR ? offc : offf) + (size_t)e * NO * NO * NO;
 #define JM(o, i) (TR ? m.J[(i) * PC + (o)] : m.J[(o) * PC + (i)])
