@@ -677,9 +677,10 @@ static int launch_transfer(int nelem, const double *hJ, const int *offc, const i
   return 0;
 }
 
-// (P, Q) pairs instantiated: every level of p-MG hierarchies up to degree 4 with qextra 0/1
+// (P, Q) pairs instantiated: every level of p-MG hierarchies up to degree 4 (Q <= 5); anything
+// else runs through the generic restriction/basis/QFunction kernels
 #define B200_FOR_PQ(X) \
-  X(2, 2) X(2, 3) X(3, 3) X(2, 4) X(3, 4) X(4, 4) X(2, 5) X(3, 5) X(4, 5) X(5, 5) X(2, 6) X(3, 6) X(5, 6)
+  X(2, 2) X(2, 3) X(3, 3) X(2, 4) X(3, 4) X(4, 4) X(2, 5) X(3, 5) X(4, 5) X(5, 5)
 
 template <int PROB, int MODE>
 static int dispatch_apply(int P, int Q, const Material &mt, int nelem, const double *hB, const double *hD,

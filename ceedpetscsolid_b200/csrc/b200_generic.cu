@@ -177,9 +177,42 @@ __global__ void k_qfunction(int qf, const __grid_constant__ Material mt, int isi
   }
 }
 
+// ---- B.5 diagonal, generic path: one (din, cin) unit-input pass ------------------------
+// ediag[e][cin][n] += sum_q sum_dout G_dout[q,n] * dv[e][dout*3+cin][q] * G_din[q,n]
+__global__ void k_diag_accumulate(int nelem, int P, int Q, const double *__restrict__ B, const double *__restrict__ D,
+                                  int din, int cin, const double *__restrict__ dv, double *__restrict__ ediag) {
+  const int P3 = P * P * P, Q3 = Q * Q * Q;
+  const size_t total = (size_t)nelem * P3;
+  GRID_STRIDE(i, total) {
+    const int n = (int)(i % P3);
+    const size_t e = i / P3;
+    const int nx = n % P, ny = (n / P) % P, nz = n / (P * P);
+    double acc = 0;
+    for (int q = 0; q < Q3; q++) {
+      const int qx = q % Q, qy = (q / Q) % Q, qz = q / (Q * Q);
+      const double bx = B[qx * P + nx], by = B[qy * P + ny], bz = B[qz * P + nz];
+      const double dx = D[qx * P + nx], dy = D[qy * P + ny], dz = D[qz * P + nz];
+      const double g[3] = {dx * by * bz, bx * dy * bz, bx * by * dz};
+      double s = 0;
+      for (int dout = 0; dout < 3; dout++) s += g[dout] * dv[(e * 9 + dout * 3 + cin) * Q3 + q];
+      acc += s * g[din];
+    }
+    ediag[(e * 3 + cin) * P3 + n] += acc;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_diag_accumulate(int nelem, int P, int Q, const double *d_interp1d, const double *d_grad1d, int din,
+                                    int cin, const double *d_dv, double *d_ediag) {
+  const size_t total = (size_t)nelem * P * P * P;
+  if (!total) return 0;
+  k_diag_accumulate<<<grid_for(total, 128), 128, 0, g_stream>>>(nelem, P, Q, d_interp1d, d_grad1d, din, cin, d_dv, d_ediag);
+  B200_LAUNCH_CHECK("k_diag_accumulate");
+  return 0;
+}
 
 extern "C" int b200_restrict_offsets(int transpose, int nelem, int elemsize, int ncomp, int compstride,
                                      const int *d_offsets, const double *d_in, double *d_out) {

@@ -43,6 +43,9 @@ __global__ void k_scatter_set(double *dst, const int *idx, const double *src, si
 __global__ void k_scatter_add(double *dst, const int *idx, const double *src, size_t n) {
   GRID_STRIDE(i, n) atomicAdd(dst + idx[i], src[i]);
 }
+__global__ void k_fill_strided(double *d, double v, size_t n, size_t stride, size_t count) {
+  GRID_STRIDE(i, n * count) d[(i / n) * stride + i % n] = v;
+}
 __global__ void k_mask_zero(double *d, const int *idx, size_t n) { GRID_STRIDE(i, n) d[idx[i]] = 0.0; }
 
 // deterministic two-pass reductions (fixed grid, fixed tree): mode 0 dot, 1 sum|x|, 2 max|x|
@@ -188,6 +191,9 @@ int b200_vec_norm_host(const double *x, size_t n, int norm_type, double *hresult
 int b200_gather(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_gather<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
 int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_set<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
 int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_add<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
+int b200_fill_strided(double *d, double v, size_t n, size_t stride, size_t count) {
+  VEC_KERNEL((k_fill_strided<<<grid_for(n * count, 256), 256, 0, g_stream>>>(d, v, n, stride, count)), n * count);
+}
 int b200_mask_zero(double *d, const int *idx, size_t n) { VEC_KERNEL((k_mask_zero<<<grid_for(n, 256), 256, 0, g_stream>>>(d, idx, n)), n); }
 
 int b200_elems_per_block(int Q) { return elems_per_block(Q); }

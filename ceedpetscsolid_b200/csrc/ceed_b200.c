@@ -902,7 +902,8 @@ static int grow(Ceed ceed, double **buf, size_t *have, size_t need) {
   return 0;
 }
 
-static int op_apply_generic(CeedOperator op, CeedVector in, CeedVector out) {
+/* element / quadrature-point counts of a generic operator */
+static int op_counts(CeedOperator op, CeedInt *nelem_out, CeedInt *nq_out) {
   Ceed ceed = op->ceed;
   CeedQFunction qf = op->qf;
   CeedInt nelem = 0, nq = 0;
@@ -919,41 +920,55 @@ static int op_apply_generic(CeedOperator op, CeedVector in, CeedVector out) {
     for (int i = 0; i < qf->nin && !nq; i++)
       if (op->in[i].r && op->in[i].r != CEED_ELEMRESTRICTION_NONE) nq = op->in[i].r->elemsize;
   if (!nelem || !nq) return CeedError(ceed, 1, "operator %s: cannot determine element / quadrature counts", qf->name);
+  *nelem_out = nelem;
+  *nq_out = nq;
+  return 0;
+}
 
-  const double *qin[MAXF];
-  double *qout[MAXF];
-  for (int i = 0; i < qf->nin; i++) {
-    OpField *f = &op->in[i];
-    const CeedEvalMode em = qf->in[i].emode;
-    const size_t qsz = sizeof(double) * (size_t)nelem * qf->in[i].size * nq;
-    if (em == CEED_EVAL_WEIGHT) {
-      if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_WEIGHT needs a basis", qf->in[i].name);
-      CeedChk(grow(ceed, &op->qbuf[i], &op->qbytes[i], qsz));
-      CeedChk(basis_apply_raw(f->b, nelem, 0, CEED_EVAL_WEIGHT, NULL, op->qbuf[i]));
-      qin[i] = op->qbuf[i];
-      continue;
-    }
-    CeedVector src = f->v == CEED_VECTOR_ACTIVE ? in : f->v;
-    if (!src || src == CEED_VECTOR_NONE) return CeedError(ceed, 1, "field \"%s\" has no input vector", qf->in[i].name);
-    if (!f->r || f->r == CEED_ELEMRESTRICTION_NONE) return CeedError(ceed, 1, "field \"%s\" needs an element restriction", qf->in[i].name);
-    const double *l;
-    CeedChk(vec_dev_read(src, &l));
-    const size_t esz = sizeof(double) * (size_t)nelem * f->r->ncomp * f->r->elemsize;
-    CeedChk(grow(ceed, &op->ebuf[i], &op->ebytes[i], esz));
-    CeedChk(rstr_apply_raw(f->r, 0, l, op->ebuf[i]));
-    if (em == CEED_EVAL_NONE) {
-      if (f->r->elemsize != nq || f->r->ncomp != qf->in[i].size)
-        return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_NONE size mismatch", qf->in[i].name);
-      qin[i] = op->ebuf[i];
-    } else {
-      if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": eval mode needs a tensor basis", qf->in[i].name);
-      if (qf->in[i].size != f->b->ncomp * (em == CEED_EVAL_GRAD ? 3 : 1))
-        return CeedError(ceed, 1, "field \"%s\": QFunction size %d does not match basis", qf->in[i].name, qf->in[i].size);
-      CeedChk(grow(ceed, &op->qbuf[i], &op->qbytes[i], qsz));
-      CeedChk(basis_apply_raw(f->b, nelem, 0, em, op->ebuf[i], op->qbuf[i]));
-      qin[i] = op->qbuf[i];
-    }
+/* Q-vector of input field i (restriction + basis); `in` feeds active fields.  With
+ * skip_active the active fields are left to the caller (diagonal assembly). */
+static int op_input_qvec(CeedOperator op, int i, CeedVector in, CeedInt nelem, CeedInt nq, int skip_active,
+                         const double **q) {
+  Ceed ceed = op->ceed;
+  CeedQFunction qf = op->qf;
+  OpField *f = &op->in[i];
+  const CeedEvalMode em = qf->in[i].emode;
+  const size_t qsz = sizeof(double) * (size_t)nelem * qf->in[i].size * nq;
+  *q = NULL;
+  if (em == CEED_EVAL_WEIGHT) {
+    if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_WEIGHT needs a basis", qf->in[i].name);
+    CeedChk(grow(ceed, &op->qbuf[i], &op->qbytes[i], qsz));
+    CeedChk(basis_apply_raw(f->b, nelem, 0, CEED_EVAL_WEIGHT, NULL, op->qbuf[i]));
+    *q = op->qbuf[i];
+    return 0;
   }
+  if (f->v == CEED_VECTOR_ACTIVE && skip_active) return 0;
+  CeedVector src = f->v == CEED_VECTOR_ACTIVE ? in : f->v;
+  if (!src || src == CEED_VECTOR_NONE) return CeedError(ceed, 1, "field \"%s\" has no input vector", qf->in[i].name);
+  if (!f->r || f->r == CEED_ELEMRESTRICTION_NONE) return CeedError(ceed, 1, "field \"%s\" needs an element restriction", qf->in[i].name);
+  const double *l;
+  CeedChk(vec_dev_read(src, &l));
+  const size_t esz = sizeof(double) * (size_t)nelem * f->r->ncomp * f->r->elemsize;
+  CeedChk(grow(ceed, &op->ebuf[i], &op->ebytes[i], esz));
+  CeedChk(rstr_apply_raw(f->r, 0, l, op->ebuf[i]));
+  if (em == CEED_EVAL_NONE) {
+    if (f->r->elemsize != nq || f->r->ncomp != qf->in[i].size)
+      return CeedError(ceed, 1, "field \"%s\": CEED_EVAL_NONE size mismatch", qf->in[i].name);
+    *q = op->ebuf[i];
+  } else {
+    if (!is_tensor3(f->b)) return CeedError(ceed, 1, "field \"%s\": eval mode needs a tensor basis", qf->in[i].name);
+    if (qf->in[i].size != f->b->ncomp * (em == CEED_EVAL_GRAD ? 3 : 1))
+      return CeedError(ceed, 1, "field \"%s\": QFunction size %d does not match basis", qf->in[i].name, qf->in[i].size);
+    CeedChk(grow(ceed, &op->qbuf[i], &op->qbytes[i], qsz));
+    CeedChk(basis_apply_raw(f->b, nelem, 0, em, op->ebuf[i], op->qbuf[i]));
+    *q = op->qbuf[i];
+  }
+  return 0;
+}
+
+static int op_run_qfunction(CeedOperator op, CeedInt nelem, CeedInt nq, const double **qin, double **qout) {
+  Ceed ceed = op->ceed;
+  CeedQFunction qf = op->qf;
   for (int i = 0; i < qf->nout; i++) {
     const size_t qsz = sizeof(double) * (size_t)nelem * qf->out[i].size * nq;
     CeedChk(grow(ceed, &op->qbuf[MAXF + i], &op->qbytes[MAXF + i], qsz));
@@ -963,6 +978,18 @@ static int op_apply_generic(CeedOperator op, CeedVector in, CeedVector out) {
   const int id = qf->qf_id;
   if (id != B200_QF_SETUPGEO && id != B200_QF_IDENTITY) CeedChk(qf_physics(qf, &phys));
   B2(ceed, b200_qfunction_apply(id, &phys, qf->identity_size, nelem, nq, qf->nin, qin, qf->nout, qout));
+  return 0;
+}
+
+static int op_apply_generic(CeedOperator op, CeedVector in, CeedVector out) {
+  Ceed ceed = op->ceed;
+  CeedQFunction qf = op->qf;
+  CeedInt nelem = 0, nq = 0;
+  CeedChk(op_counts(op, &nelem, &nq));
+  const double *qin[MAXF];
+  double *qout[MAXF];
+  for (int i = 0; i < qf->nin; i++) CeedChk(op_input_qvec(op, i, in, nelem, nq, 0, &qin[i]));
+  CeedChk(op_run_qfunction(op, nelem, nq, qin, qout));
   for (int i = 0; i < qf->nout; i++) {
     OpField *f = &op->out[i];
     const CeedEvalMode em = qf->out[i].emode;
@@ -983,6 +1010,51 @@ static int op_apply_generic(CeedOperator op, CeedVector in, CeedVector out) {
     }
     CeedChk(rstr_apply_raw(f->r, 1, e, l));
   }
+  return 0;
+}
+
+/* Generic CeedOperatorLinearAssembleAddDiagonal (App. B.5) for operators of the Jacobian shape:
+ * one active GRAD input and one active GRAD output on the same restriction and basis.  Nine
+ * unit-input QFunction passes, each folded into the element diagonal on the device. */
+static int op_diagonal_generic(CeedOperator op, CeedVector assembled) {
+  Ceed ceed = op->ceed;
+  CeedQFunction qf = op->qf;
+  int ia = -1, oa = -1;
+  for (int i = 0; i < qf->nin; i++)
+    if (op->in[i].v == CEED_VECTOR_ACTIVE) ia = ia < 0 ? i : -2;
+  for (int i = 0; i < qf->nout; i++)
+    if (op->out[i].v == CEED_VECTOR_ACTIVE) oa = oa < 0 ? i : -2;
+  if (ia < 0 || oa < 0 || qf->nout != 1 || qf->in[ia].emode != CEED_EVAL_GRAD || qf->out[oa].emode != CEED_EVAL_GRAD ||
+      qf->in[ia].size != 9 || qf->out[oa].size != 9 || !is_tensor3(op->in[ia].b) || op->in[ia].r != op->out[oa].r ||
+      !op->in[ia].r || op->in[ia].r == CEED_ELEMRESTRICTION_NONE)
+    return CeedError(ceed, 1, "%s: CeedOperatorLinearAssembleDiagonal supports operators with one active 3-component "
+                              "GRAD input and output on the same restriction (QFunction %s does not qualify)",
+                     CEED_B200_RESOURCE, qf->name);
+  CeedInt nelem = 0, nq = 0;
+  CeedChk(op_counts(op, &nelem, &nq));
+  CeedBasis b = op->in[ia].b;
+  CeedElemRestriction r = op->in[ia].r;
+  CeedChk(basis_device(b));
+  const double *qin[MAXF];
+  double *qout[MAXF];
+  for (int i = 0; i < qf->nin; i++) CeedChk(op_input_qvec(op, i, NULL, nelem, nq, 1, &qin[i]));
+  const size_t usz = sizeof(double) * (size_t)nelem * 9 * nq, esz = sizeof(double) * (size_t)nelem * 3 * r->elemsize;
+  CeedChk(grow(ceed, &op->qbuf[ia], &op->qbytes[ia], usz));
+  CeedChk(grow(ceed, &op->ebuf[MAXF + oa], &op->ebytes[MAXF + oa], esz));
+  double *unit = op->qbuf[ia], *ediag = op->ebuf[MAXF + oa];
+  qin[ia] = unit;
+  B2(ceed, b200_memset(ediag, 0, esz));
+  for (int din = 0; din < 3; din++)
+    for (int cin = 0; cin < 3; cin++) {
+      B2(ceed, b200_memset(unit, 0, usz));
+      /* unit field (din, cin): Q-vector layout [elem][9][nq], component index din*3 + cin */
+      B2(ceed, b200_fill_strided(unit + (size_t)(din * 3 + cin) * nq, 1.0, nq, (size_t)9 * nq, nelem));
+      CeedChk(op_run_qfunction(op, nelem, nq, qin, qout));
+      B2(ceed, b200_diag_accumulate(nelem, b->P, b->Q, b->d_interp1d, b->d_grad1d, din, cin, qout[oa], ediag));
+    }
+  double *l;
+  CeedChk(vec_dev_rw(assembled, &l));
+  CeedChk(rstr_apply_raw(r, 1, ediag, l));
   return 0;
 }
 
@@ -1057,8 +1129,7 @@ int CeedOperatorLinearAssembleAddDiagonal(CeedOperator op, CeedVector assembled,
   }
   if (op->kind == OP_UNSET) CeedChk(op_setup(op));
   if (op->kind != OP_FUSED_JACOBIAN && !(op->kind == OP_FUSED_RESIDUAL && op->problem == B200_PROB_LINELAS))
-    return CeedError(ceed, 1, "%s: CeedOperatorLinearAssembleDiagonal is implemented for the Jacobian operators (QFunction %s is not one)",
-                     CEED_B200_RESOURCE, op->qf->name);
+    return op_diagonal_generic(op, assembled);
   OpField *u = &op->in[0];
   b200_physics phys;
   CeedChk(qf_physics(op->qf, &phys));

@@ -1,0 +1,140 @@
+"""Halo exchange for brick-partitioned box meshes: the PetscSF stand-in behind
+DMGlobalToLocal(INSERT_VALUES) / DMLocalToGlobal(ADD_VALUES) (/root/reference/src/matops.c:33,57).
+
+DMPlexDistribute with overlap 0 (/root/reference/src/setupdm.c:58-64) partitions ELEMENTS; mesh
+nodes on partition interfaces are duplicated in the local vectors and owned by exactly one rank.
+Here the partition is a grid of bricks and an interface node is owned by the LOWEST rank that
+holds it.  Two collective steps, both neighbour point-to-point (<= 26 neighbours, 7 for 2x2x2):
+
+  owner_to_ghost(Xloc)      owners send interface values, ghosts overwrite   (G2L, INSERT)
+  ghost_to_owner_add(Yloc)  ghosts send partial sums, owners accumulate       (L2G, ADD)
+
+Interface dofs are packed / unpacked with libceed_b200.so kernels (b200_gather,
+b200_scatter_set, b200_scatter_add) and moved with torch.distributed batch_isend_irecv
+(NCCL over NVLink for CUDA tensors, gloo for the CPU tests).
+"""
+import numpy as np
+import torch
+
+
+def _ranges(mesh_n, grid, p):
+    """Per axis: node index range [lo, hi] (inclusive, global numbering) of every brick."""
+    out = []
+    for d in range(3):
+        q, rem = divmod(mesh_n[d], grid[d])
+        r = []
+        for i in range(grid[d]):
+            start = i * q + min(i, rem)
+            size = q + (1 if i < rem else 0)
+            r.append((start * p, (start + size) * p))
+        out.append(r)
+    return out
+
+
+class Halo:
+    def __init__(self, gmesh, grid, rank, p, dist=None, device=None, ncomp=3):
+        self.dist, self.rank, self.grid, self.p = dist, rank, grid, p
+        px, py, pz = grid
+        rng = _ranges(gmesh.n, grid, p)
+        me = (rank % px, (rank // px) % py, rank // (px * py))
+        lo = [rng[d][me[d]][0] for d in range(3)]
+        hi = [rng[d][me[d]][1] for d in range(3)]
+        N = [hi[d] - lo[d] + 1 for d in range(3)]  # local nodes per axis
+        self.nnodes = N[0] * N[1] * N[2]
+        owner = np.full((N[2], N[1], N[0]), rank, dtype=np.int64)
+        # shared[r] = local node indices (in a canonical GLOBAL order) shared with neighbour r
+        self.neighbours = []
+        shared = {}
+        lidx = np.arange(self.nnodes).reshape(N[2], N[1], N[0])
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    if dx == dy == dz == 0:
+                        continue
+                    nb = (me[0] + dx, me[1] + dy, me[2] + dz)
+                    if not all(0 <= nb[d] < grid[d] for d in range(3)):
+                        continue
+                    r = nb[0] + px * (nb[1] + py * nb[2])
+                    sl = []
+                    for d, dd in enumerate((dx, dy, dz)):
+                        # overlap of my node range with the neighbour's along axis d
+                        a = max(lo[d], rng[d][nb[d]][0]); b = min(hi[d], rng[d][nb[d]][1])
+                        assert a <= b
+                        sl.append(slice(a - lo[d], b - lo[d] + 1))
+                    ids = lidx[sl[2], sl[1], sl[0]].reshape(-1)  # z,y,x order == global lexicographic order
+                    shared[r] = ids
+                    sub = owner[sl[2], sl[1], sl[0]]
+                    np.minimum(sub, r, out=sub)
+                    self.neighbours.append(r)
+        self.neighbours.sort()
+        self.owned_node_mask = (owner == rank).reshape(-1)
+        own = owner.reshape(-1)
+        dev = device if device is not None else ("cuda" if torch.cuda.is_available() and dist is not None and dist.get_backend() == "nccl" else "cpu")
+        self.device = torch.device(dev)
+
+        def dofs(nodes):
+            return (nodes[:, None] * ncomp + np.arange(ncomp)[None, :]).reshape(-1).astype(np.int32)
+
+        # owner -> ghost: I send the nodes I own that r holds; I receive the nodes r owns
+        # ghost -> owner: the reverse.  Both ranks enumerate a shared set in the same global order.
+        self.send_own, self.recv_ghost = {}, {}
+        for r in self.neighbours:
+            ids = shared[r]
+            mine = ids[own[ids] == rank]
+            theirs = ids[own[ids] == r]
+            if mine.size:
+                self.send_own[r] = torch.from_numpy(dofs(mine)).to(self.device)
+            if theirs.size:
+                self.recv_ghost[r] = torch.from_numpy(dofs(theirs)).to(self.device)
+        self._buf = {}
+
+    def _buffers(self, key, idx, like):
+        k = (key, like.dtype)
+        if k not in self._buf:
+            self._buf[k] = {r: torch.empty(i.numel(), dtype=like.dtype, device=like.device) for r, i in idx.items()}
+        return self._buf[k]
+
+    @staticmethod
+    def _gather(dst, src, idx):
+        if src.is_cuda:
+            from .ceed import b2, lib
+            b2(lib.b200_gather(dst.data_ptr(), src.data_ptr(), idx.data_ptr(), idx.numel()))
+        else:
+            torch.index_select(src, 0, idx.long(), out=dst)
+
+    @staticmethod
+    def _scatter(dst, idx, src, add):
+        if dst.is_cuda:
+            from .ceed import b2, lib
+            f = lib.b200_scatter_add if add else lib.b200_scatter_set
+            b2(f(dst.data_ptr(), idx.data_ptr(), src.data_ptr(), idx.numel()))
+        elif add:
+            dst.index_add_(0, idx.long(), src)
+        else:
+            dst.index_copy_(0, idx.long(), src)
+
+    def _exchange(self, vec, send_idx, recv_idx, add, tag):
+        dist = self.dist
+        sbuf = self._buffers("s" + tag, send_idx, vec)
+        rbuf = self._buffers("r" + tag, recv_idx, vec)
+        for r, idx in send_idx.items():
+            self._gather(sbuf[r], vec, idx)
+        ops = []
+        for r in self.neighbours:  # same global order on every rank
+            if r in recv_idx:
+                ops.append(dist.P2POp(dist.irecv, rbuf[r], r))
+            if r in send_idx:
+                ops.append(dist.P2POp(dist.isend, sbuf[r], r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for r, idx in recv_idx.items():
+            self._scatter(vec, idx, rbuf[r], add)
+
+    def owner_to_ghost(self, Xloc):
+        """DMGlobalToLocal part 2: ghosts receive the owner's value."""
+        self._exchange(Xloc, self.send_own, self.recv_ghost, add=False, tag="o2g")
+
+    def ghost_to_owner_add(self, Yloc):
+        """DMLocalToGlobal(ADD_VALUES) part 1: owners accumulate the ghosts' partial sums."""
+        self._exchange(Yloc, self.recv_ghost, self.send_own, add=True, tag="g2o")

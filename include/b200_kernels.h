@@ -85,13 +85,16 @@ int b200_gather(double *dst, const double *src, const int *idx, size_t n);      
 int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n);   /* dst[idx[i]]=src[i] */
 int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n);   /* dst[idx[i]]+=src[i] */
 int b200_mask_zero(double *d, const int *idx, size_t n);                          /* d[idx[i]] = 0 */
+/* `count` runs of `n` entries, `stride` apart, set to `value` */
+int b200_fill_strided(double *d, double value, size_t n, size_t stride, size_t count);
 
 /* ---- layout of CEED_STRIDES_BACKEND vectors (setuplibceed.c:304-318) --------------- */
 /* The backend owns this layout.  For elemsize = Q^3 (2 <= Q <= 8) it is "q-blocked":
  * elements in groups of EB = b200_elems_per_block(Q); inside group g holding ebn
- * elements (ebn = EB except in the tail group):
- *   index(e,c,q) = g*EB*ncomp*Q^3 + (c*Q + q%Q)*(ebn*Q^2) + (e%EB)*Q^2 + q/Q
- * i.e. [group][comp][qx][elem-in-group][qy + Q*qz]; otherwise plain [elem][comp][node]. */
+ * elements (ebn = EB except in the tail group), with q = qx + Q*t, t = qy + Q*qz:
+ *   index(e,c,q) = g*EB*ncomp*Q^3 + (c*Q + qx)*(ebn*Q^2) + t*ebn + (e % EB)
+ * i.e. [group][comp][qx][t][elem-in-group]: the fused kernels' lane id (t*ebn + e) walks
+ * contiguous memory for every (comp, qx).  Otherwise plain [elem][comp][node]. */
 int b200_elems_per_block(int Q);
 int b200_strided_layout_q(int elemsize);  /* returns Q if the blocked layout applies, else 0 */
 
@@ -117,6 +120,12 @@ int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double *d_interp1
 /* in[k] / out[k]: device Q-vectors [elem][size_k][nq] in field declaration order */
 int b200_qfunction_apply(int qf_id, const b200_physics *phys, int identity_size, int nelem, int nq,
                          int nin, const double *const *d_in, int nout, double *const *d_out);
+
+/* generic-path piece of CeedOperatorLinearAssembleDiagonal (App. B.5): one unit-input pass,
+ * ediag[e][cin][n] += sum_q sum_dout G_dout[q,n] dv[e][dout*3+cin][q] G_din[q,n]
+ * (dv = QFunction output for the unit field (din, cin); G_d = Kronecker gradient matrices) */
+int b200_diag_accumulate(int nelem, int P, int Q, const double *d_interp1d, const double *d_grad1d, int din,
+                         int cin, const double *d_dv, double *d_ediag);
 
 /* ---- hot path: fused CeedOperatorApply (matops.c:46; setuplibceed.c:518-542,818-839) */
 /* y_L += E^T G^T D G E x_L in ONE kernel: offsets gather, sum-factorised gradient

@@ -35,7 +35,8 @@ def test_setupgeo_residual_jacobian_diagonal(G, problem, n, p, qextra, perm):
     yg = g.residual()
     if perm is not None:
         tmp = np.empty_like(yo).reshape(-1, 3); tmp[g.perm] = yo.reshape(-1, 3); yo = tmp.reshape(-1)
-    assert g.fine.opApply.is_fused
+    fused_expected = (p + 1 + qextra) <= 5  # fused kernels are instantiated for Q <= 5
+    assert g.fine.opApply.is_fused == fused_expected
     assert rel_err(yg, yo) < TOL
     if o.has_gradu:
         gu = g.strided_to_plain(g.fine.ErestrictGradui, g.fine.gradu)
@@ -52,7 +53,7 @@ def test_setupgeo_residual_jacobian_diagonal(G, problem, n, p, qextra, perm):
             def P(v):
                 t = np.empty_like(v).reshape(-1, 3); t[g.perm] = v.reshape(-1, 3); return t.reshape(-1)
             xg, yo, do = P(x), P(yo), P(do)
-        assert g.data[level].opJacob.is_fused
+        assert g.data[level].opJacob.is_fused == fused_expected
         assert rel_err(g.jacobian(level, xg), yo) < TOL, (level, deg)
         assert rel_err(g.diagonal(level), do) < TOL, (level, deg)
 
