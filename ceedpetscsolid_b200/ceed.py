@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libceed_b200.so")
+LIBPATH = os.environ.get("CEED_B200_LIB", os.path.join(HERE, "libceed_b200.so"))  # override: tuning builds only
 
 MEM_HOST, MEM_DEVICE = 0, 1
 COPY_VALUES, USE_POINTER, OWN_POINTER = 0, 1, 2

@@ -27,7 +27,12 @@ int set_error_msg(const char *msg);
   } while (0)
 
 // elements per thread block of the fused kernels == group size of the q-blocked layout
-__host__ __device__ constexpr int elems_per_block(int Q) { return Q <= 3 ? 16 : 8; }
+// (Q >= 4: 4 elements x Q^2 threads = 64 / 100 threads per CTA: many small independent CTAs per SM
+// hide the per-stage barriers and load latencies better than fewer large ones -- measured)
+#ifndef B200_EB_BIG
+#define B200_EB_BIG 4
+#endif
+__host__ __device__ constexpr int elems_per_block(int Q) { return Q <= 3 ? 16 : B200_EB_BIG; }
 
 // Index of (element e, component c, point q) in a q-blocked backend-strided vector:
 // groups of EB elements; inside a group holding ebn elements (ebn = EB except in the tail)

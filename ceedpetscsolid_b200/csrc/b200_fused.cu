@@ -37,14 +37,15 @@ template <int Q> struct Cfg {
   static constexpr int NT = ((T * EB + 31) / 32) * 32;
   static constexpr int Q3 = Q * Q * Q;
   // Shared-memory lattice with ODD strides (1, QP, QP^2) and lanes ordered element-fastest
-  // (tid = t*EB + e): a half-warp then holds EB=16 elements of one line, or 8 elements of two
-  // neighbouring lines whose offsets differ by an odd number; with the element stride SE odd
-  // (EB=16) or = 2 mod 16 (EB=8) every 64-bit shared access of every line orientation is
-  // bank-conflict free (checked exhaustively in tests/test_layout.py).
+  // (tid = t*EB + e): a half-warp then holds EB=16 elements of one line, or 16/EB neighbouring
+  // lines of EB elements whose lattice offsets are distinct mod 16/EB; with the element stride SE
+  // odd (EB=16) or = 16/EB mod 16 (EB=8, 4) every 64-bit shared access of every line orientation
+  // is bank-conflict free (checked exhaustively in tests/test_abi_and_layout.py).
   static constexpr int QP = (Q % 2) ? Q : Q + 1;
   static constexpr int SY = QP, SZ = QP * QP, SC = QP * QP * QP;
   static constexpr int SE0 = 9 * SC;
-  static constexpr int SE = EB == 8 ? SE0 + ((2 - SE0 % 16) + 16) % 16 : (SE0 | 1);
+  static constexpr int SEM = 16 / EB;  // EB=8: SE = 2 mod 16, EB=4: SE = 4 mod 16, EB=16: odd
+  static constexpr int SE = EB == 16 ? (SE0 | 1) : SE0 + ((SEM - SE0 % 16) + 16) % 16;
   static constexpr size_t SMEM = (size_t)EB * SE * sizeof(double);
 };
 
@@ -60,7 +61,7 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) 
 enum { MODE_RESIDUAL = 0, MODE_JACOBIAN = 1 };
 
 template <int P, int Q, int PROB, int MODE>
-__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? 2 : 1)
+__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? 4 : 2) : 1)
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y) {

@@ -44,7 +44,7 @@ def test_no_cpu_fallback_and_loud_failure_without_gpu():
 
 
 def _eb(Q):
-    return 16 if Q <= 3 else 8
+    return 16 if Q <= 3 else 4
 
 
 def _qblocked(nelem, ncomp, Q, e, c, q):
@@ -65,12 +65,12 @@ def test_qblocked_layout_is_a_bijection(Q, nelem, ncomp):
 
 @pytest.mark.parametrize("Q", [2, 3, 4, 5])
 def test_shared_lattice_is_bank_conflict_free(Q):
-    """tid = t*EB + e, odd lattice strides (1, QP, QP^2), element stride SE = 2 mod 16 (EB=8) or odd
-    (EB=16): every half-warp of every line orientation touches 16 distinct 8-byte banks."""
+    """tid = t*EB + e, odd lattice strides (1, QP, QP^2), element stride SE = 16/EB mod 16 (EB=8, 4) or
+    odd (EB=16): every half-warp of every line orientation touches 16 distinct 8-byte banks."""
     EB = _eb(Q)
     QP = Q if Q % 2 else Q + 1
     SE = 9 * QP ** 3
-    SE = SE + ((2 - SE % 16) + 16) % 16 if EB == 8 else SE | 1
+    SE = SE + ((16 // EB - SE % 16) + 16) % 16 if EB < 16 else SE | 1
     T = Q * Q
     for orient in "xyz":
         for w in range(0, T * EB, 16):
