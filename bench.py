@@ -253,8 +253,9 @@ def main():
     if os.path.exists(traffic_path):
         with open(traffic_path) as f:
             tj = json.load(f)
-        if tj.get("elements") == mesh.nelem:
-            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+        # one `ncu --set full` capture on a 32^3 box; traffic is per element, scaled to this launch
+        roofline["traffic"] = tj.get("dram_bytes_per_element", 0) * mesh.nelem or None
+        roofline["traffic_source"] = tj.get("source")
 
     # ---- e2e: the libCEED boundary with HOST buffers (-memtype host): SetArray(HOST), Apply, TakeArray(HOST)
     e2e = None
