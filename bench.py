@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--degree", type=int, default=4)
     ap.add_argument("--n", type=int, default=64, help="elements per direction per GPU (weak) / of the whole box (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--n-cpu", type=int, default=16, help="box size of the bounded CPU sample")
+    ap.add_argument("--n-cpu", type=int, default=20, help="box size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -144,6 +144,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        config["elements_per_gpu"] = args.n ** 3
+        config["bricks"] = "1x1x1" if world == 1 else "x".join(map(str, __import__("ceedpetscsolid_b200.mesh", fromlist=["grid_for"]).grid_for(world)))
         steps = max(1, min(args.steps, 20))
         cb = cpu_leg(problem, p, args.n_cpu, steps, min(args.warmup, 2))
         line = {"impl": "reference", "metric": "GDoF/s of hyperFS Jacobian MatMult at p=4", "value": cb["value"],

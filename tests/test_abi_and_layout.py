@@ -81,3 +81,26 @@ def test_shared_lattice_is_bank_conflict_free(Q):
                 off = {"x": b * QP * QP + a * QP, "y": b * QP * QP + a, "z": b * QP + a}[orient]
                 banks.add((e * SE + off) % 16)
             assert len(banks) == min(16, T * EB - w), (orient, w)
+
+
+def _build_capi(tmp):
+    import subprocess
+    exe = os.path.join(tmp, "capi_smoke")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-O1", "-Wall", "-Werror=implicit-function-declaration",
+                    "-Wno-unused-parameter", "-Wno-unused-variable", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "capi_smoke.c"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "ceedpetscsolid_b200"), "-lceed_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "ceedpetscsolid_b200"), "-lm"], check=True)
+    return exe
+
+
+def test_c_program_written_against_ceed_h_compiles_and_links(tmp_path):
+    """the reference's call sequence (setuplibceed.c / matops.c) in plain C99 against <ceed.h>"""
+    assert os.path.exists(_build_capi(str(tmp_path)))
+
+
+@pytest.mark.gpu
+def test_c_program_runs_on_the_gpu(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_capi(str(tmp_path))], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "capi_smoke OK" in r.stdout, r.stdout + r.stderr
