@@ -43,6 +43,21 @@ __global__ void k_scatter_set(double *dst, const int *idx, const double *src, si
 __global__ void k_scatter_add(double *dst, const int *idx, const double *src, size_t n) {
   GRID_STRIDE(i, n) atomicAdd(dst + idx[i], src[i]);
 }
+__global__ void k_gather_or_zero(double *dst, const double *src, const int *idx, size_t n) {
+  GRID_STRIDE(i, n) { const int j = idx[i]; dst[i] = j >= 0 ? src[j] : 0.0; }
+}
+// ELL sparse mat-vec (slot-major storage): y[r] = sum_s vals[s*n + r] * x[cols[s*n + r]], cols < 0 = empty
+__global__ void k_ell_spmv(size_t n, int nslots, const int *__restrict__ cols, const double *__restrict__ vals,
+                           const double *__restrict__ x, double *__restrict__ y) {
+  GRID_STRIDE(r, n) {
+    double s = 0;
+    for (int k = 0; k < nslots; k++) {
+      const int c = cols[(size_t)k * n + r];
+      if (c >= 0) s += vals[(size_t)k * n + r] * x[c];
+    }
+    y[r] = s;
+  }
+}
 __global__ void k_fill_strided(double *d, double v, size_t n, size_t stride, size_t count) {
   GRID_STRIDE(i, n * count) d[(i / n) * stride + i % n] = v;
 }
@@ -191,6 +206,10 @@ int b200_vec_norm_host(const double *x, size_t n, int norm_type, double *hresult
 int b200_gather(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_gather<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
 int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_set<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
 int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_add<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
+int b200_gather_or_zero(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_gather_or_zero<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
+int b200_ell_spmv(size_t n, int nslots, const int *cols, const double *vals, const double *x, double *y) {
+  VEC_KERNEL((k_ell_spmv<<<grid_for(n, 128), 128, 0, g_stream>>>(n, nslots, cols, vals, x, y)), n);
+}
 int b200_fill_strided(double *d, double v, size_t n, size_t stride, size_t count) {
   VEC_KERNEL((k_fill_strided<<<grid_for(n * count, 256), 256, 0, g_stream>>>(d, v, n, stride, count)), n * count);
 }

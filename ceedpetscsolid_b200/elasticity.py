@@ -1,0 +1,162 @@
+"""The mini-app driver on the `/gpu/b200` backend: what /root/reference/elasticity.c `main` does
+between CeedInit (:110) and the end of the load-increment loop (:676), for synthetic box meshes.
+
+  set-up           elasticity.c:132-281  -> setuplibceed.setup_all, matops.LevelDM per level
+  MatShell ctxs    elasticity.c:386-452  -> matops.setup_jacobian_ctx / setup_prolong_restrict_ctx
+  solver config    elasticity.c:498-603  -> solver.PMultigrid + solver.pcg
+  solve            elasticity.c:632-676  -> solver.newton_solve
+  clamp BCs        src/boundary.c:53-74  -> bc_clamp (same expression, including its precedence quirk)
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ceed as libceed
+from . import matops, setuplibceed, solver
+from .mesh import BoxMesh, grid_for
+
+
+def bc_clamp(coords, load, clamp):
+    """BCClamp (src/boundary.c:53-74): clamp = [tx,ty,tz, kx,ky,kz, theta/pi] (translate, axis, rotation)."""
+    x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+    lx, ly, lz = (clamp[i] * load for i in range(3))
+    kx, ky, kz = clamp[3], clamp[4], clamp[5]
+    theta = clamp[6] * math.pi * load
+    c, s = math.cos(theta), math.sin(theta)
+    u = np.empty_like(coords)
+    u[:, 0] = lx + s * (-kz * y + ky * z) + (1 - c) * (-ky * ky + kz * kz * x + kx * ky * y + kx * kz * z)
+    u[:, 1] = ly + s * (kz * x + -kx * z) + (1 - c) * (kx * ky * x - (kx * kx + kz * kz) * y + ky * kz * z)
+    u[:, 2] = lz + s * (-ky * x + kx * y) + (1 - c) * (kx * kz * x + ky * kz * y - (kx * kx + ky * ky) * z)
+    return u
+
+
+@dataclass
+class AppCtx:
+    """The options of /root/reference/src/cloptions.c that matter here."""
+    problem: str = "hyperFS"
+    degree: int = 4
+    n: tuple = (8, 8, 8)
+    nu: float = 0.3
+    E: float = 1.0
+    qextra: int = 0
+    multigrid: str = "logarithmic"
+    num_steps: int = 10
+    perturb: float = 0.0
+    # clamped faces: (axis, side) -> [tx,ty,tz, kx,ky,kz, theta/pi]  (-bc_clamp, -bc_clamp_N_translate/_rotate)
+    clamp: dict = field(default_factory=lambda: {(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
+
+
+class GpuLevel:
+    """One p-multigrid level on the /gpu/b200 backend (the MatShell of elasticity.c:392-411)."""
+
+    def __init__(self, dm, user, res_user=None):
+        self.dm, self.user, self.res_user = dm, user, res_user
+        self.n, self.device = dm.nglobal, dm.device
+
+    def jacobian(self, X, Y):
+        matops.ApplyJacobian_Ceed(self.user, X, Y)
+
+    def diagonal(self, D):
+        matops.GetDiag_Ceed(self.user, D)
+
+    def local_apply(self, xloc, yloc):
+        u = self.user
+        u.Xceed.set_array(xloc, u.memType)
+        u.Yceed.set_array(yloc, u.memType)
+        u.op.apply(u.Xceed, u.Yceed)
+        u.Xceed.take_array(u.memType)
+        u.Yceed.take_array(u.memType)
+
+    def residual(self, U, F, load):
+        self.res_user.loadIncrement = load
+        matops.FormResidual_Ceed(U, F, self.res_user)
+
+
+class GpuTransfer:
+    def __init__(self, pr):
+        self.pr = pr
+
+    def prolong(self, Xc, Yf):
+        matops.Prolong_Ceed(self.pr, Xc, Yf)
+
+    def restrict(self, Xf, Yc):
+        matops.Restrict_Ceed(self.pr, Xf, Yc)
+
+
+class Elasticity:
+    """Builds the whole solver stack for one rank (one GPU)."""
+
+    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None):
+        self.app, self.dist = app, dist
+        grid = grid_for(world)
+        self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
+        self.mesh = self.gmesh.brick(grid, rank) if world > 1 else self.gmesh
+        self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}")
+        self.degrees, self.data, self.phys = setuplibceed.setup_all(self.ceed, self.mesh, app.problem, app.degree, app.nu,
+                                                                    app.E, app.qextra, app.multigrid)
+        faces = list(app.clamp.keys())
+        self.dms, self.users = [], []
+        for l, deg in enumerate(self.degrees):
+            halo = None
+            if world > 1:
+                from .halo import Halo
+                halo = Halo(self.gmesh, grid, rank, deg, dist)
+            dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}")
+            self.dms.append(dm)
+            self.users.append(matops.setup_jacobian_ctx(dm, self.ceed, self.data[l], self.phys))
+        fine = len(self.degrees) - 1
+        fu = self.users[fine]
+        # resCtx = shallow copy of the fine Jacobian ctx with op = opApply (elasticity.c:420-425)
+        self.res_user = matops.UserMult(dm=fu.dm, Xloc=fu.Xloc, Yloc=fu.Yloc, Xceed=fu.Xceed, Yceed=fu.Yceed,
+                                        op=self.data[fine].opApply, qf=self.data[fine].qfApply, ceed=self.ceed,
+                                        phys=self.phys, memType=fu.memType, bc_values=self._bc_values_fn(self.dms[fine], app))
+        self.levels = [GpuLevel(self.dms[l], self.users[l], self.res_user if l == fine else None)
+                       for l in range(len(self.degrees))]
+        self.transfers = [None]
+        for l in range(1, len(self.degrees)):
+            pr = matops.setup_prolong_restrict_ctx(self.dms[l - 1], self.dms[l], self.ceed, self.data[l - 1], self.data[l],
+                                                   self.users[l - 1], self.users[l])
+            self.transfers.append(GpuTransfer(pr))
+        self.V = solver.Vec(dist if world > 1 else None)
+        self.pc = solver.PMultigrid(self.V, self.levels, self.transfers)
+        self.U = self.dms[fine].create_global_vector()
+
+    @staticmethod
+    def _bc_values_fn(dm, app):
+        """DMPlexInsertBoundaryValues stand-in: clamp values at the Dirichlet nodes for a load fraction."""
+        p = dm.degree
+        coords = dm.mesh.node_coords(p)
+        bc_nodes = np.flatnonzero(dm.bc_nodes)
+        xyz = coords[bc_nodes]
+        face_of = np.full(bc_nodes.size, -1)
+        for fi, (axis, side) in enumerate(app.clamp.keys()):  # later faces win on shared edges, as DMAddBoundary order
+            on = dm.mesh.boundary_mask(p, [(axis, side)])[bc_nodes]
+            face_of[on] = fi
+        clamps = list(app.clamp.values())
+
+        def values(load):
+            u = np.zeros((bc_nodes.size, 3))
+            for fi, cl in enumerate(clamps):
+                m = face_of == fi
+                if m.any():
+                    u[m] = bc_clamp(xyz[m], load, cl)
+            return torch.from_numpy(u.reshape(-1)).to(dm.device)
+
+        return values
+
+    def solve(self, log=None, **kw):
+        self.U.zero_()
+        fine = self.levels[-1]
+        out = solver.newton_solve(self.V, fine, self.pc, self.U, num_increments=self.app.num_steps, log=log, **kw)
+        out["dofs_global_unconstrained"] = self._global_unconstrained()
+        # "DoFs/Sec in SNES" = global dofs x total KSP iterations / solve time (elasticity.c:762-764), in MDoF/s
+        out["mdofs_per_sec_in_snes"] = 1e-6 * out["dofs_global_unconstrained"] * out["ksp_its"] / max(out["time_s"], 1e-12)
+        return out
+
+    def _global_unconstrained(self):
+        n = torch.tensor([self.dms[-1].nglobal], dtype=torch.float64, device=self.dms[-1].device)
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(n)
+        return int(n.item())

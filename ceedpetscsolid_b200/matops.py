@@ -45,6 +45,9 @@ class LevelDM:
         bc_idx = np.flatnonzero(np.repeat(bc_nodes, 3)).astype(np.int32)
         self.nglobal = fo_idx.size
         self.free_owned_idx = torch.from_numpy(fo_idx).to(self.device)
+        l2g = np.full(self.lsize, -1, dtype=np.int32)  # local dof -> global dof (-1: ghost or Dirichlet)
+        l2g[fo_idx] = np.arange(fo_idx.size, dtype=np.int32)
+        self.local_to_global_idx = torch.from_numpy(l2g).to(self.device)
         self.bc_idx = torch.from_numpy(bc_idx).to(self.device)
         self._fo_host, self._bc_host = fo_idx, bc_idx
 
@@ -67,6 +70,17 @@ class LevelDM:
             Xloc.numpy()[self._fo_host] = X.numpy()
         if self.halo is not None:
             self.halo.owner_to_ghost(Xloc)
+
+    def zero_and_global_to_local(self, X, Xloc):
+        """VecZeroEntries(Xloc) followed by DMGlobalToLocal(INSERT_VALUES) (matops.c:106 + :33) in one
+        pass over Xloc (device vectors); identical result, one third of the memory traffic."""
+        if Xloc.is_cuda:
+            b2(lib.b200_gather_or_zero(Xloc.data_ptr(), X.data_ptr(), self.local_to_global_idx.data_ptr(), self.lsize))
+            if self.halo is not None:
+                self.halo.owner_to_ghost(Xloc)
+        else:
+            Xloc.zero_()
+            self.global_to_local(X, Xloc)
 
     def local_to_global(self, Yloc, Y):
         """VecZeroEntries(Y); DMLocalToGlobal(dm, Yloc, ADD_VALUES, Y): constrained dofs dropped."""
@@ -112,10 +126,14 @@ def setup_jacobian_ctx(dm, ceed, data, phys, physSmoother=None, memType=MEM_DEVI
                     physSmoother=physSmoother, memType=memType)
 
 
-def ApplyLocalCeedOp(X, Y, user):
-    """matops.c:26-60: Y = P^T A_loc P X."""
-    user.dm.global_to_local(X, user.Xloc)                         # :33
-    user.Yloc.zero_()                                             # :34
+def ApplyLocalCeedOp(X, Y, user, zero_xloc=False):
+    """matops.c:26-60: Y = P^T A_loc P X.  zero_xloc fuses the caller's VecZeroEntries(Xloc)
+    (ApplyJacobian_Ceed, matops.c:106) into the global-to-local pass."""
+    if zero_xloc:
+        user.dm.zero_and_global_to_local(X, user.Xloc)            # :106 + :33
+    else:
+        user.dm.global_to_local(X, user.Xloc)                     # :33
+    # :34 VecZeroEntries(Yloc) is subsumed: CeedOperatorApply zeroes its output vector itself
     user.Xceed.set_array(user.Xloc, user.memType, USE_POINTER)    # :40
     user.Yceed.set_array(user.Yloc, user.memType, USE_POINTER)    # :41
     user.op.apply(user.Xceed, user.Yceed)                         # :46
@@ -135,8 +153,7 @@ def FormResidual_Ceed(X, Y, user):
 
 def ApplyJacobian_Ceed(user, X, Y):
     """matops.c:98-112 (and ApplyJacobianCoarse_Ceed :82-95): zero boundary values, apply."""
-    user.Xloc.zero_()
-    ApplyLocalCeedOp(X, Y, user)
+    ApplyLocalCeedOp(X, Y, user, zero_xloc=True)
 
 
 def GetDiag_Ceed(user, D):

@@ -1,0 +1,396 @@
+"""Newton-Krylov-p-multigrid harness: the PETSc pieces the reference configures in
+/root/reference/elasticity.c:378-603 and drives in :632-676, restated so that the operator
+apply can be turned into "SNES solve time" without PETSc:
+
+  outer KSP      preconditioned CG, natural norm sqrt(r.z), rtol 1e-10, zero initial guess  (:504-507)
+  PC             PCMG multiplicative V-cycle, 3 pre + 3 post smoothing steps per level      (:588-590)
+  smoother       Chebyshev + point-Jacobi; lambda_max estimated by a few CG steps on the
+                 Jacobi-preconditioned level operator, interval [0.1, 1.1] * lambda_max     (:539-552)
+  coarse level   p = 1 operator ASSEMBLED by colouring its (linear) action                   (src/misc.c:151-183)
+                 reference: GAMG on the AIJ matrix; here: Jacobi-PCG on the assembled ELL matrix
+  SNES           Newton with load increments, warm start, rtol 1e-8                          (:595-601,:637-673)
+
+Differences from PETSc that are inherent (hard part 11): GAMG and PETSc's noisy-rhs PRNG
+are not reproducible outside PETSc; the eigen-estimate rhs here is a seeded deterministic vector, the
+coarse solve is Jacobi-PCG, the line search is a backtracking search on |F|.  Iteration counts are therefore
+compared between the GPU operators and the CPU oracle under THIS harness (tests/test_gpu_solver.py).
+
+The algorithms are written once over a small "level operations" interface; vectors are torch
+tensors.  On CUDA tensors every vector operation is a libceed_b200.so kernel; on CPU tensors
+(oracle runs) torch/numpy is used.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from .ceed import b2, lib
+
+# --------------------------------------------------------------------------- vector kernels
+
+
+class Vec:
+    """BLAS-1 on torch tensors; CUDA tensors go through libceed_b200.so kernels."""
+
+    def __init__(self, dist=None):
+        self.dist = dist
+        self._scratch = None
+
+    def dot(self, a, b):
+        if a.is_cuda:
+            if self._scratch is None:
+                self._scratch = torch.zeros(1, dtype=torch.float64, device=a.device)
+            b2(lib.b200_vec_dot(a.data_ptr(), b.data_ptr(), a.numel(), self._scratch.data_ptr()))
+            s = self._scratch
+        else:
+            s = torch.dot(a, b).reshape(1)
+        if self.dist is not None and self.dist.get_world_size() > 1:
+            s = s.clone()
+            self.dist.all_reduce(s)
+        return float(s.item())
+
+    @staticmethod
+    def axpy(y, alpha, x):  # y += alpha x
+        if y.is_cuda:
+            b2(lib.b200_vec_axpy(y.data_ptr(), float(alpha), x.data_ptr(), y.numel()))
+        else:
+            y.add_(x, alpha=float(alpha))
+
+    @staticmethod
+    def aypx(y, alpha, x):  # y = x + alpha y
+        if y.is_cuda:
+            b2(lib.b200_vec_aypx(y.data_ptr(), float(alpha), x.data_ptr(), y.numel()))
+        else:
+            y.mul_(float(alpha)).add_(x)
+
+    @staticmethod
+    def axpby(z, a, x, b, y):  # z = a x + b y
+        if z.is_cuda:
+            b2(lib.b200_vec_axpby(z.data_ptr(), float(a), x.data_ptr(), float(b), y.data_ptr(), z.numel()))
+        else:
+            torch.add(x * float(a), y, alpha=float(b), out=z)
+
+    @staticmethod
+    def pmult(w, x, y):  # w = x .* y
+        if w.is_cuda:
+            b2(lib.b200_vec_pointwise_mult(w.data_ptr(), x.data_ptr(), y.data_ptr(), w.numel()))
+        else:
+            torch.mul(x, y, out=w)
+
+    @staticmethod
+    def scale(x, a):
+        if x.is_cuda:
+            b2(lib.b200_vec_scale(x.data_ptr(), float(a), x.numel()))
+        else:
+            x.mul_(float(a))
+
+    @staticmethod
+    def copy(dst, src):
+        dst.copy_(src)
+
+    @staticmethod
+    def zero(x):
+        x.zero_()
+
+
+# --------------------------------------------------------------------------- Krylov / smoothers
+
+
+def pcg(V, A, b, x, M=None, rtol=1e-10, atol=1e-50, maxit=10000, work=None, hist=None):
+    """Preconditioned CG with the natural norm sqrt(r.z) (KSPCG + KSP_NORM_NATURAL, elasticity.c:504-507).
+    x is the initial guess and the result.  A(x, y): y = A x.  M(r, z): z = M^-1 r (None: identity).
+    Returns (iterations, converged_reason, final natural residual norm)."""
+    r, z, p, Ap = work if work is not None else [torch.zeros_like(b) for _ in range(4)]
+    A(x, Ap)
+    V.axpby(r, 1.0, b, -1.0, Ap)
+    if M is None:
+        V.copy(z, r)
+    else:
+        M(r, z)
+    rz = V.dot(r, z)
+    r0 = math.sqrt(abs(rz))
+    if hist is not None:
+        hist.append(r0)
+    if r0 <= atol or r0 == 0.0:
+        return 0, "atol", r0
+    V.copy(p, z)
+    for it in range(1, maxit + 1):
+        A(p, Ap)
+        pAp = V.dot(p, Ap)
+        if pAp <= 0:
+            return it, "indefinite", math.sqrt(abs(rz))
+        alpha = rz / pAp
+        V.axpy(x, alpha, p)
+        V.axpy(r, -alpha, Ap)
+        if M is None:
+            V.copy(z, r)
+        else:
+            M(r, z)
+        rz_new = V.dot(r, z)
+        rn = math.sqrt(abs(rz_new))
+        if hist is not None:
+            hist.append(rn)
+        if rn <= max(rtol * r0, atol):
+            return it, "rtol", rn
+        V.aypx(p, rz_new / rz, z)
+        rz = rz_new
+    return maxit, "maxit", math.sqrt(abs(rz))
+
+
+def estimate_lambda_max(V, A, dinv, n, device, its=10, seed=0):
+    """Largest eigenvalue of D^-1 A from `its` CG (Lanczos) steps with a deterministic rhs
+    (KSPChebyshevEstEigSet + noisy rhs, elasticity.c:540-545; PETSc's PRNG is not reproducible here)."""
+    g = torch.Generator().manual_seed(1234 + seed)
+    b = torch.rand(n, dtype=torch.float64, generator=g).to(device) - 0.5
+    x = torch.zeros_like(b)
+    r, z, p, Ap = (torch.zeros_like(b) for _ in range(4))
+    V.copy(r, b)
+    V.pmult(z, dinv, r)
+    V.copy(p, z)
+    rz = V.dot(r, z)
+    alphas, betas = [], []
+    for _ in range(its):
+        A(p, Ap)
+        pAp = V.dot(p, Ap)
+        if pAp <= 0 or rz == 0:
+            break
+        alpha = rz / pAp
+        V.axpy(x, alpha, p)
+        V.axpy(r, -alpha, Ap)
+        V.pmult(z, dinv, r)
+        rz_new = V.dot(r, z)
+        beta = rz_new / rz
+        alphas.append(alpha)
+        betas.append(beta)
+        V.aypx(p, beta, z)
+        rz = rz_new
+        if rz_new == 0:
+            break
+    k = len(alphas)
+    T = np.zeros((k, k))
+    for i in range(k):
+        T[i, i] = 1.0 / alphas[i] + (betas[i - 1] / alphas[i - 1] if i > 0 else 0.0)
+        if i + 1 < k:
+            T[i, i + 1] = T[i + 1, i] = math.sqrt(betas[i]) / alphas[i]
+    return float(np.linalg.eigvalsh(T).max())
+
+
+class ChebyshevJacobi:
+    """KSPCHEBYSHEV + PCJACOBI smoother with eigenvalue interval [0.1, 1.1] * lambda_max (elasticity.c:539-552)."""
+
+    def __init__(self, V, A, n, device, its=3, seed=0):
+        self.V, self.A, self.its, self.n, self.device, self.seed = V, A, its, n, device, seed
+        self.dinv = None
+        self.emax = self.emin = None
+        self.r, self.z, self.d, self.Ad = (torch.zeros(n, dtype=torch.float64, device=device) for _ in range(4))
+
+    def setup(self, diag):
+        """PCJacobi set-up (MatGetDiagonal -> GetDiag_Ceed) + eigen-estimate; once per Newton step."""
+        self.dinv = 1.0 / diag
+        lmax = estimate_lambda_max(self.V, self.A, self.dinv, self.n, self.device, seed=self.seed)
+        self.emin, self.emax = 0.1 * lmax, 1.1 * lmax
+
+    def apply(self, b, x, zero_guess):
+        V, A = self.V, self.A
+        theta, delta = 0.5 * (self.emax + self.emin), 0.5 * (self.emax - self.emin)
+        sigma = theta / delta
+        rho = 1.0 / sigma
+        r, z, d, Ad = self.r, self.z, self.d, self.Ad
+        if zero_guess:
+            V.zero(x)
+            V.copy(r, b)
+        else:
+            A(x, Ad)
+            V.axpby(r, 1.0, b, -1.0, Ad)
+        V.pmult(z, self.dinv, r)
+        V.axpby(d, 1.0 / theta, z, 0.0, z)
+        for k in range(self.its):
+            V.axpy(x, 1.0, d)
+            if k + 1 == self.its:
+                break
+            A(d, Ad)
+            V.axpy(r, -1.0, Ad)
+            V.pmult(z, self.dinv, r)
+            rho_new = 1.0 / (2.0 * sigma - rho)
+            V.axpby(d, rho_new * rho, d, 2.0 * rho_new / delta, z)
+            rho = rho_new
+
+
+# --------------------------------------------------------------------------- coarse level by colouring
+
+
+class ColoredCoarseMatrix:
+    """FormJacobian (src/misc.c:151-183): the coarse (p = 1) Jacobian assembled from its action on
+    coloured unit vectors -- exact because the action is linear.  Assembled on the LOCAL vector
+    space of the rank (27 node colours x 3 components = 81 operator applies, one ELL slot each);
+    the global action is P^T A_loc P with the same halo exchange as the matrix-free operator."""
+
+    def __init__(self, dm, local_apply):
+        self.dm, self.local_apply = dm, local_apply
+        N = dm.mesh.nodes_per_dim(1)
+        self.N = N
+        n = dm.lsize
+        dev = dm.device
+        k, j, i = np.meshgrid(np.arange(N[2]), np.arange(N[1]), np.arange(N[0]), indexing="ij")
+        self.ijk = [a.reshape(-1) for a in (i, j, k)]
+        self.cols = torch.full((81, n), -1, dtype=torch.int32, device=dev)
+        self.vals = torch.zeros((81, n), dtype=torch.float64, device=dev)
+        self.x = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.y = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.seeds = []
+        nn = N[0] * N[1] * N[2]
+        for color in range(27):
+            cc = (color % 3, (color // 3) % 3, color // 9)
+            tgt = []
+            ok = np.ones(nn, bool)
+            for d in range(3):
+                off = ((cc[d] - self.ijk[d] % 3 + 1) % 3) - 1  # in {-1,0,1}: neighbour of that colour along d
+                t = self.ijk[d] + off
+                ok &= (t >= 0) & (t < N[d])
+                tgt.append(t)
+            colnode = tgt[0] + N[0] * (tgt[1] + N[1] * tgt[2])
+            seed_nodes = np.flatnonzero((self.ijk[0] % 3 == cc[0]) & (self.ijk[1] % 3 == cc[1]) & (self.ijk[2] % 3 == cc[2]))
+            for a in range(3):
+                s = color * 3 + a
+                col = np.where(ok, colnode * 3 + a, -1).astype(np.int32)
+                self.cols[s] = torch.from_numpy(np.repeat(col, 3)).to(dev)
+                self.seeds.append(torch.from_numpy((seed_nodes * 3 + a).astype(np.int64)).to(dev))
+        self.Xloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.Yloc = torch.zeros(n, dtype=torch.float64, device=dev)
+
+    def assemble(self):
+        """81 local operator applies (ApplyJacobianCoarse_Ceed without the halo: A_loc itself)."""
+        for s in range(81):
+            self.x.zero_()
+            self.x[self.seeds[s]] = 1.0
+            self.local_apply(self.x, self.y)
+            self.vals[s].copy_(self.y)
+        self.vals.mul_((self.cols >= 0).to(torch.float64))
+
+    def mult(self, X, Y):
+        dm = self.dm
+        dm.zero_and_global_to_local(X, self.Xloc)
+        if self.Xloc.is_cuda:
+            b2(lib.b200_ell_spmv(dm.lsize, 81, self.cols.data_ptr(), self.vals.data_ptr(), self.Xloc.data_ptr(),
+                                 self.Yloc.data_ptr()))
+        else:
+            c = self.cols.long().clamp_min(0)
+            self.Yloc.copy_((self.vals * self.Xloc[c] * (self.cols >= 0)).sum(0))
+        dm.local_to_global(self.Yloc, Y)
+
+
+# --------------------------------------------------------------------------- PCMG + Newton
+
+
+class PMultigrid:
+    """PCMG, multiplicative V-cycle, levels[0] = coarsest (p = 1) ... levels[-1] = finest."""
+
+    def __init__(self, V, levels, transfers, coarse_rtol=1e-3, coarse_maxit=500, smooth_its=3):
+        """levels: list of objects with .n, .device, .jacobian(X, Y), .diagonal(D), .local_apply(xloc, yloc), .dm
+        transfers[l] (l >= 1): object with .prolong(Xc, Yf), .restrict(Xf, Yc) between l-1 and l."""
+        self.V, self.levels, self.transfers = V, levels, transfers
+        self.coarse_rtol, self.coarse_maxit = coarse_rtol, coarse_maxit
+        L = len(levels)
+        self.smoothers = [None] + [ChebyshevJacobi(V, levels[l].jacobian, levels[l].n, levels[l].device, smooth_its, seed=l)
+                                   for l in range(1, L)]
+        mk = lambda l: torch.zeros(levels[l].n, dtype=torch.float64, device=levels[l].device)
+        self.b = [mk(l) for l in range(L)]
+        self.x = [mk(l) for l in range(L)]
+        self.r = [mk(l) for l in range(L)]
+        self.t = [mk(l) for l in range(L)]
+        self.diag = [mk(l) for l in range(L)]
+        self.coarse = ColoredCoarseMatrix(levels[0].dm, levels[0].local_apply)
+        self.cwork = [mk(0) for _ in range(4)]
+        self.cdinv = mk(0)
+        self.coarse_its = 0
+        self.coarse_solves = 0
+
+    def setup(self):
+        """Once per Newton step (SNESComputeJacobian -> FormJacobian + PCSetUp): diagonals, eigen-estimates,
+        coarse assembly."""
+        for l, lev in enumerate(self.levels):
+            lev.diagonal(self.diag[l])
+            if l > 0:
+                self.smoothers[l].setup(self.diag[l])
+        self.coarse.assemble()
+        self.cdinv.copy_(1.0 / self.diag[0])
+
+    def _coarse_solve(self, b, x):
+        V = self.V
+        x.zero_()
+        its, _, _ = pcg(V, self.coarse.mult, b, x, M=lambda r, z: V.pmult(z, self.cdinv, r), rtol=self.coarse_rtol,
+                        maxit=self.coarse_maxit, work=self.cwork)
+        self.coarse_its += its
+        self.coarse_solves += 1
+
+    def _cycle(self, l):
+        V = self.V
+        if l == 0:
+            self._coarse_solve(self.b[0], self.x[0])
+            return
+        sm, lev, tr = self.smoothers[l], self.levels[l], self.transfers[l]
+        sm.apply(self.b[l], self.x[l], zero_guess=True)                 # pre-smooth
+        lev.jacobian(self.x[l], self.t[l])
+        V.axpby(self.r[l], 1.0, self.b[l], -1.0, self.t[l])             # residual
+        tr.restrict(self.r[l], self.b[l - 1])
+        self._cycle(l - 1)
+        tr.prolong(self.x[l - 1], self.t[l])
+        V.axpy(self.x[l], 1.0, self.t[l])                               # coarse-grid correction
+        sm.apply(self.b[l], self.x[l], zero_guess=False)                # post-smooth
+
+    def apply(self, r, z):
+        L = len(self.levels) - 1
+        self.b[L].copy_(r)
+        self._cycle(L)
+        z.copy_(self.x[L])
+
+
+def newton_solve(V, fine, pc, U, num_increments=10, snes_rtol=1e-8, snes_atol=1e-50, snes_maxit=50, ksp_rtol=1e-10,
+                 ksp_maxit=200, log=None):
+    """Load-increment loop + Newton (elasticity.c:637-673).  fine.residual(U, F, load) evaluates
+    FormResidual_Ceed at load fraction `load` (and refreshes gradu); the Jacobian operators then
+    linearise about that state.  Returns a summary dict (iteration counts as in elasticity.c:684-749)."""
+    n, dev = fine.n, fine.device
+    F, dU = (torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(2))
+    work = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(4)]
+    total_snes = total_ksp = 0
+    per_step = []
+    t0 = time.perf_counter()
+    for inc in range(1, num_increments + 1):
+        load = inc / num_increments
+        fine.residual(U, F, load)
+        fnorm0 = fnorm = math.sqrt(V.dot(F, F))
+        its = 0
+        while its < snes_maxit and fnorm > max(snes_rtol * fnorm0, snes_atol):
+            pc.setup()
+            dU.zero_()
+            k, reason, _ = pcg(V, fine.jacobian, F, dU, M=pc.apply, rtol=ksp_rtol, maxit=ksp_maxit, work=work)
+            # backtracking line search on |F| (stand-in for SNES line search "cp", elasticity.c:595-601):
+            # full step first, halve while the residual norm does not decrease
+            lam, taken = 1.0, 0.0
+            for _ in range(6):
+                V.axpy(U, -(lam - taken), dU)
+                taken = lam
+                fine.residual(U, F, load)
+                fnew = math.sqrt(V.dot(F, F))
+                if math.isfinite(fnew) and fnew < (1.0 - 1e-4 * lam) * fnorm:
+                    break
+                lam *= 0.5
+            fnorm = fnew
+            its += 1
+            total_ksp += k
+            if log:
+                log(f"  load {load:.2f} newton {its}: |F| = {fnorm:.3e}  ksp its {k} ({reason})")
+            if not math.isfinite(fnorm):
+                break
+        total_snes += its
+        per_step.append((its, fnorm / fnorm0 if fnorm0 else 0.0))
+        if not math.isfinite(fnorm) or fnorm > max(snes_rtol * fnorm0, snes_atol):
+            break
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    converged = len(per_step) == num_increments and all(
+        math.isfinite(rel) and rel <= max(snes_rtol, 1e-300) for _, rel in per_step)
+    return {"snes_its": total_snes, "ksp_its": total_ksp, "time_s": time.perf_counter() - t0, "converged": converged,
+            "per_step": per_step, "coarse_its": pc.coarse_its, "coarse_solves": pc.coarse_solves}

@@ -85,6 +85,12 @@ int b200_gather(double *dst, const double *src, const int *idx, size_t n);      
 int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n);   /* dst[idx[i]]=src[i] */
 int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n);   /* dst[idx[i]]+=src[i] */
 int b200_mask_zero(double *d, const int *idx, size_t n);                          /* d[idx[i]] = 0 */
+/* VecZeroEntries(Xloc) + DMGlobalToLocal(INSERT) in one pass (matops.c:106,33):
+ * dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (idx = local dof -> global dof, -1 for ghost / Dirichlet dofs) */
+int b200_gather_or_zero(double *dst, const double *src, const int *idx, size_t n);
+/* assembled coarse-level operator (FormJacobian by colouring, src/misc.c:151-183) in slot-major ELL:
+ * y[r] = sum_s vals[s*n + r] * x[cols[s*n + r]]   (cols < 0 = empty slot) */
+int b200_ell_spmv(size_t n, int nslots, const int *cols, const double *vals, const double *x, double *y);
 /* `count` runs of `n` entries, `stride` apart, set to `value` */
 int b200_fill_strided(double *d, double value, size_t n, size_t stride, size_t count);
 

@@ -1,0 +1,79 @@
+"""Newton-Krylov-p-MG harness: host logic on the CPU oracle (no GPU), and GPU-vs-oracle parity of
+iteration counts and of the solution under the same harness."""
+import numpy as np
+import pytest
+import torch
+
+from ceedpetscsolid_b200 import solver
+from ceedpetscsolid_b200.elasticity import AppCtx, bc_clamp
+
+
+def test_pcg_and_chebyshev_on_a_small_spd_matrix():
+    rng = np.random.default_rng(0)
+    n = 60
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.linspace(1.0, 50.0, n)
+    Am = torch.from_numpy(Q @ np.diag(lam) @ Q.T)
+    A = lambda x, y: y.copy_(Am @ x)
+    V = solver.Vec()
+    b = torch.from_numpy(rng.standard_normal(n))
+    x = torch.zeros(n, dtype=torch.float64)
+    its, reason, _ = solver.pcg(V, A, b, x, rtol=1e-12)
+    assert reason == "rtol" and its <= n
+    assert torch.linalg.norm(Am @ x - b) < 1e-9 * torch.linalg.norm(b)
+    dinv = 1.0 / torch.diagonal(Am)
+    lmax = solver.estimate_lambda_max(V, A, dinv, n, torch.device("cpu"), its=30)
+    true = np.linalg.eigvalsh((torch.diag(dinv) @ Am).numpy().astype(float)).real.max() if False else \
+        np.max(np.real(np.linalg.eigvals(torch.diag(dinv).numpy() @ Am.numpy())))
+    assert abs(lmax - true) < 0.05 * true
+    sm = solver.ChebyshevJacobi(V, A, n, torch.device("cpu"), its=3)
+    sm.setup(torch.diagonal(Am).clone())
+    x0 = torch.zeros(n, dtype=torch.float64)
+    sm.apply(b, x0, zero_guess=True)
+    e0 = torch.linalg.norm(torch.linalg.solve(Am, b))
+    e1 = torch.linalg.norm(x0 - torch.linalg.solve(Am, b))
+    assert e1 < e0  # a smoother reduces the error
+
+
+def test_bc_clamp_matches_reference_expression():
+    """src/boundary.c:53-74 incl. its precedence quirk in the first component"""
+    xyz = np.array([[0.3, 0.7, 1.0]])
+    cl = [0.1, -0.2, 0.05, 0.0, 0.0, 1.0, 0.25]
+    u = bc_clamp(xyz, 0.5, cl)[0]
+    x, y, z = xyz[0]
+    th = 0.25 * np.pi * 0.5
+    c, s = np.cos(th), np.sin(th)
+    kx, ky, kz = 0.0, 0.0, 1.0
+    assert np.isclose(u[0], 0.05 + s * (-kz * y + ky * z) + (1 - c) * (-ky * ky + kz * kz * x + kx * ky * y + kx * kz * z))
+    assert np.isclose(u[1], -0.1 + s * (kz * x - kx * z) + (1 - c) * (kx * ky * x - (kx * kx + kz * kz) * y + ky * kz * z))
+    assert np.isclose(u[2], 0.025)
+
+
+@pytest.mark.parametrize("problem,degree,steps", [("linElas", 2, 1), ("hyperFS", 2, 2)])
+def test_newton_krylov_pmg_converges_on_the_oracle(problem, degree, steps):
+    from oracle_levels import oracle_solve
+    app = AppCtx(problem=problem, degree=degree, n=(3, 3, 3), num_steps=steps)
+    out, U = oracle_solve(app)
+    assert out["converged"], out
+    assert out["snes_its"] >= steps and out["ksp_its"] > 0
+    if problem == "linElas":
+        assert out["snes_its"] <= 2  # linear problem: one Newton step (+ at most one check step)
+    assert out["ksp_its"] / out["snes_its"] < 40  # p-MG preconditioned CG, mesh-independent-ish counts
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,degree,n,steps", [("hyperFS", 2, (4, 4, 4), 2), ("hyperSS", 3, (3, 3, 3), 1),
+                                                    ("hyperFS", 4, (2, 2, 3), 2)])
+def test_gpu_and_oracle_agree_on_iteration_counts_and_solution(problem, degree, n, steps):
+    from ceedpetscsolid_b200.elasticity import Elasticity
+    from oracle_levels import oracle_solve
+    app = AppCtx(problem=problem, degree=degree, n=n, num_steps=steps, perturb=0.05,
+                 clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0.01, 0, -0.04, 0, 0, 1, 0.02]})
+    ref, Uref = oracle_solve(app)
+    el = Elasticity(app)
+    out = el.solve()
+    assert out["converged"] and ref["converged"]
+    assert out["snes_its"] == ref["snes_its"], (out, ref)
+    assert out["ksp_its"] == ref["ksp_its"], (out, ref)
+    u = el.U.cpu().numpy()
+    assert np.linalg.norm(u - Uref.numpy()) < 1e-9 * np.linalg.norm(Uref.numpy())
