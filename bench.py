@@ -114,6 +114,45 @@ def cpu_leg(problem, p, n_cpu, steps, warmup):
             "ms_per_apply": dt * 1e3}
 
 
+def solve_bench(args, rank, world, local_rank, dist, config):
+    """BASELINE configs[4]: full Newton-Krylov-p-MG solve, hyperFS, 10 load steps, Chebyshev/Jacobi smoothing
+    with GPU diagonal assembly; wall time of the load-increment loop only, max over ranks
+    (/root/reference/elasticity.c:632-676,755-764)."""
+    import torch
+    from ceedpetscsolid_b200 import ceed as libceed
+    from ceedpetscsolid_b200.elasticity import AppCtx, Elasticity
+    from ceedpetscsolid_b200.mesh import BoxMesh, grid_for
+    grid = grid_for(world)
+    n = (args.n * grid[0], args.n * grid[1], args.n * grid[2]) if args.scaling == "weak" else (args.n,) * 3
+    app = AppCtx(problem=args.problem, degree=args.degree, n=n, num_steps=args.load_steps, perturb=0.05,
+                 clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
+    el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank)
+    libceed.launch_count_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    out = el.solve(log=(lambda m: print(m, file=sys.stderr)) if rank == 0 else None)
+    t = torch.tensor([out["time_s"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.result()
+    if rank == 0:
+        config.update({"workload": f"{args.problem} degree {args.degree} Newton-Krylov-pMG solve, box {args.n}^3 per GPU, "
+                                   f"{args.load_steps} load steps, levels {el.degrees}", "elements_per_gpu": el.mesh.nelem,
+                       "bricks": "x".join(map(str, grid))})
+        print(json.dumps({"metric": "SNES solve time", "value": float(t.item()), "unit": "s", "n_gpus": world, "steps": 1,
+                          "warmup": 0, "ms_per_step": float(t.item()) * 1e3, "higher_is_better": False,
+                          "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "snes_its": out["snes_its"], "ksp_its": out["ksp_its"], "converged": out["converged"],
+                          "coarse_pcg_its": out["coarse_its"], "dofs_unconstrained": out["dofs_global_unconstrained"],
+                          "mdofs_per_sec_in_snes": out["mdofs_per_sec_in_snes"], "gpu_launches": int(libceed.launch_count()),
+                          "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -127,6 +166,9 @@ def main():
     ap.add_argument("--n-cpu", type=int, default=20, help="box size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--solve", action="store_true",
+                    help="time the full Newton-Krylov-p-MG solve (BASELINE configs[4]) instead of the MatMult")
+    ap.add_argument("--load-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -163,6 +205,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.solve:
+        return solve_bench(args, rank, world, local_rank, dist, config)
     from ceedpetscsolid_b200 import ceed as libceed
     from ceedpetscsolid_b200 import matops, setuplibceed
     from ceedpetscsolid_b200.mesh import BoxMesh, grid_for, smooth_displacement

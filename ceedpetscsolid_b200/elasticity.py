@@ -73,6 +73,14 @@ class GpuLevel:
         self.res_user.loadIncrement = load
         matops.FormResidual_Ceed(U, F, self.res_user)
 
+    def bc_increment_rhs(self, F, load_prev, load):
+        """F = P^T A_loc(U) [0; u_bc(load) - u_bc(load_prev)]: the Jacobian applied to the boundary increment."""
+        u, r = self.user, self.res_user
+        u.Xloc.zero_()
+        u.dm.insert_boundary_values(u.Xloc, r.bc_values(load) - r.bc_values(load_prev))
+        self.local_apply(u.Xloc, u.Yloc)
+        u.dm.local_to_global(u.Yloc, F)
+
 
 class GpuTransfer:
     def __init__(self, pr):

@@ -52,6 +52,12 @@ class OracleLevel:
                                      sh.qdata, sh.gradu, self.dm.lsize)
         self.dm.local_to_global(torch.from_numpy(d), D)
 
+    def bc_increment_rhs(self, F, load_prev, load):
+        self.Xloc.zero_()
+        self.dm.insert_boundary_values(self.Xloc, self.bc_values(load) - self.bc_values(load_prev))
+        self.local_apply(self.Xloc, self.Yloc)
+        self.dm.local_to_global(self.Yloc, F)
+
     def residual(self, U, F, load):
         sh = self.sh
         self.Xloc.zero_()
