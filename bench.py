@@ -21,6 +21,10 @@ import sys
 import threading
 import time
 
+# the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on STDOUT: keep stdout = one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -124,9 +128,12 @@ def solve_bench(args, rank, world, local_rank, dist, config):
     from ceedpetscsolid_b200.mesh import BoxMesh, grid_for
     grid = grid_for(world)
     n = (args.n * grid[0], args.n * grid[1], args.n * grid[2]) if args.scaling == "weak" else (args.n,) * 3
+    lengths = tuple(float(g) for g in grid) if args.scaling == "weak" else (1.0, 1.0, 1.0)
     app = AppCtx(problem=args.problem, degree=args.degree, n=n, num_steps=args.load_steps, perturb=0.05,
-                 clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
-    el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank)
+                 clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1 * lengths[2], 0, 0, 1, 0]})
+    gmesh = BoxMesh(n=n, perturb=app.perturb, seed=0, lengths=lengths)
+    el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank, gmesh=gmesh,
+                    coarse_rtol=args.coarse_rtol)
     libceed.launch_count_reset()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -146,7 +153,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                           "warmup": 0, "ms_per_step": float(t.item()) * 1e3, "higher_is_better": False,
                           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "snes_its": out["snes_its"], "ksp_its": out["ksp_its"], "converged": out["converged"],
-                          "coarse_pcg_its": out["coarse_its"], "dofs_unconstrained": out["dofs_global_unconstrained"],
+                          "coarse_pcg_its": out["coarse_its"], "coarse_rtol": args.coarse_rtol, "dofs_unconstrained": out["dofs_global_unconstrained"],
                           "mdofs_per_sec_in_snes": out["mdofs_per_sec_in_snes"], "gpu_launches": int(libceed.launch_count()),
                           "clocks": clocks}))
     if world > 1:
@@ -161,14 +168,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--problem", default="hyperFS")
     ap.add_argument("--degree", type=int, default=4)
-    ap.add_argument("--n", type=int, default=64, help="elements per direction per GPU (weak) / of the whole box (strong)")
+    ap.add_argument("--box", "--n", dest="n", type=int, default=64, help="elements per direction per GPU (weak) / of the whole box (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--n-cpu", type=int, default=20, help="box size of the bounded CPU sample")
+    ap.add_argument("--cpu-box", "--n-cpu", dest="n_cpu", type=int, default=20, help="box size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--solve", action="store_true",
                     help="time the full Newton-Krylov-p-MG solve (BASELINE configs[4]) instead of the MatMult")
     ap.add_argument("--load-steps", type=int, default=10)
+    ap.add_argument("--coarse-rtol", type=float, default=1e-3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -213,7 +221,8 @@ def main():
 
     grid = grid_for(world)
     if args.scaling == "weak":
-        gmesh = BoxMesh(n=(args.n * grid[0], args.n * grid[1], args.n * grid[2]), perturb=0.08, seed=0)
+        gmesh = BoxMesh(n=(args.n * grid[0], args.n * grid[1], args.n * grid[2]), perturb=0.08, seed=0,
+                        lengths=tuple(float(g) for g in grid))  # the domain grows with the mesh: cubic elements
     else:
         gmesh = BoxMesh(n=(args.n,) * 3, perturb=0.08, seed=0)
     mesh = gmesh.brick(grid, rank) if world > 1 else gmesh

@@ -96,7 +96,7 @@ class GpuTransfer:
 class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
-    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None):
+    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-3):
         self.app, self.dist = app, dist
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
@@ -128,7 +128,7 @@ class Elasticity:
                                                    self.users[l - 1], self.users[l])
             self.transfers.append(GpuTransfer(pr))
         self.V = solver.Vec(dist if world > 1 else None)
-        self.pc = solver.PMultigrid(self.V, self.levels, self.transfers)
+        self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol)
         self.U = self.dms[fine].create_global_vector()
 
     @staticmethod
