@@ -86,16 +86,31 @@ class Halo:
                 self.send_own[r] = torch.from_numpy(dofs(mine)).to(self.device)
             if theirs.size:
                 self.recv_ghost[r] = torch.from_numpy(dofs(theirs)).to(self.device)
+        # one contiguous pack buffer per direction: a single gather kernel packs the data for ALL
+        # neighbours, a single scatter kernel unpacks it; sends/receives are views into the buffers
+        def layout(idx):
+            ranks = [r for r in self.neighbours if r in idx]
+            cat = torch.cat([idx[r] for r in ranks]) if ranks else torch.zeros(0, dtype=torch.int32, device=self.device)
+            views, o = {}, 0
+            for r in ranks:
+                views[r] = (o, o + idx[r].numel())
+                o += idx[r].numel()
+            return cat.contiguous(), views
+
+        self.own_cat, self.own_views = layout(self.send_own)
+        self.ghost_cat, self.ghost_views = layout(self.recv_ghost)
         self._buf = {}
 
-    def _buffers(self, key, idx, like):
-        k = (key, like.dtype)
+    def _buffer(self, key, n, like):
+        k = (key, like.dtype, like.device)
         if k not in self._buf:
-            self._buf[k] = {r: torch.empty(i.numel(), dtype=like.dtype, device=like.device) for r, i in idx.items()}
+            self._buf[k] = torch.empty(n, dtype=like.dtype, device=like.device)
         return self._buf[k]
 
     @staticmethod
     def _gather(dst, src, idx):
+        if idx.numel() == 0:
+            return
         if src.is_cuda:
             from .ceed import b2, lib
             b2(lib.b200_gather(dst.data_ptr(), src.data_ptr(), idx.data_ptr(), idx.numel()))
@@ -104,6 +119,8 @@ class Halo:
 
     @staticmethod
     def _scatter(dst, idx, src, add):
+        if idx.numel() == 0:
+            return
         if dst.is_cuda:
             from .ceed import b2, lib
             f = lib.b200_scatter_add if add else lib.b200_scatter_set
@@ -113,28 +130,28 @@ class Halo:
         else:
             dst.index_copy_(0, idx.long(), src)
 
-    def _exchange(self, vec, send_idx, recv_idx, add, tag):
+    def _exchange(self, vec, send_cat, send_views, recv_cat, recv_views, add, tag):
         dist = self.dist
-        sbuf = self._buffers("s" + tag, send_idx, vec)
-        rbuf = self._buffers("r" + tag, recv_idx, vec)
-        for r, idx in send_idx.items():
-            self._gather(sbuf[r], vec, idx)
+        sbuf = self._buffer("s" + tag, send_cat.numel(), vec)
+        rbuf = self._buffer("r" + tag, recv_cat.numel(), vec)
+        self._gather(sbuf, vec, send_cat)
         ops = []
         for r in self.neighbours:  # same global order on every rank
-            if r in recv_idx:
-                ops.append(dist.P2POp(dist.irecv, rbuf[r], r))
-            if r in send_idx:
-                ops.append(dist.P2POp(dist.isend, sbuf[r], r))
+            if r in recv_views:
+                a, b = recv_views[r]
+                ops.append(dist.P2POp(dist.irecv, rbuf[a:b], r))
+            if r in send_views:
+                a, b = send_views[r]
+                ops.append(dist.P2POp(dist.isend, sbuf[a:b], r))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        for r, idx in recv_idx.items():
-            self._scatter(vec, idx, rbuf[r], add)
+        self._scatter(vec, recv_cat, rbuf, add)
 
     def owner_to_ghost(self, Xloc):
         """DMGlobalToLocal part 2: ghosts receive the owner's value."""
-        self._exchange(Xloc, self.send_own, self.recv_ghost, add=False, tag="o2g")
+        self._exchange(Xloc, self.own_cat, self.own_views, self.ghost_cat, self.ghost_views, add=False, tag="o2g")
 
     def ghost_to_owner_add(self, Yloc):
         """DMLocalToGlobal(ADD_VALUES) part 1: owners accumulate the ghosts' partial sums."""
-        self._exchange(Yloc, self.recv_ghost, self.send_own, add=True, tag="g2o")
+        self._exchange(Yloc, self.ghost_cat, self.ghost_views, self.own_cat, self.own_views, add=True, tag="g2o")
