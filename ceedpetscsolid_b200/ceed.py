@@ -131,6 +131,10 @@ _proto("b200_scatter_add", _vp, _vp, _vp, _sz)
 _proto("b200_mask_zero", _vp, _vp, _sz)
 _proto("b200_gather_or_zero", _vp, _vp, _vp, _sz)
 _proto("b200_ell_spmv", _sz, _i, _vp, _vp, _vp, _vp)
+_proto("b200_vec_axpy_dev", _vp, _vp, _sz, _vp, _vp, _d)
+_proto("b200_vec_aypx_dev", _vp, _vp, _sz, _vp, _vp)
+_proto("b200_pcg_update", _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp)
+_proto("b200_stencil27_spmv", _i, _i, _i, _vp, _vp, _vp)
 _proto("b200_vec_reciprocal", _vp, _sz)
 _proto("b200_elems_per_block", _i)
 _proto("b200_fused_supported", _i, _i)

@@ -46,6 +46,50 @@ __global__ void k_scatter_add(double *dst, const int *idx, const double *src, si
 __global__ void k_gather_or_zero(double *dst, const double *src, const int *idx, size_t n) {
   GRID_STRIDE(i, n) { const int j = idx[i]; dst[i] = j >= 0 ? src[j] : 0.0; }
 }
+// BLAS-1 with DEVICE scalars (alpha = sign * num[0] / den[0]): lets a Krylov loop run without host syncs
+__global__ void k_axpy_dev(double *y, const double *x, size_t n, const double *num, const double *den, double sign) {
+  const double a = sign * num[0] / den[0];
+  GRID_STRIDE(i, n) y[i] += a * x[i];
+}
+__global__ void k_aypx_dev(double *y, const double *x, size_t n, const double *num, const double *den) {
+  const double a = num[0] / den[0];
+  GRID_STRIDE(i, n) y[i] = x[i] + a * y[i];
+}
+// CG update in one pass: x += alpha p, r -= alpha Ap, z = dinv .* r   (alpha = rz / pAp, device scalars)
+__global__ void k_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv,
+                             size_t n, const double *rz, const double *pAp) {
+  const double a = rz[0] / pAp[0];
+  GRID_STRIDE(i, n) {
+    x[i] += a * p[i];
+    const double ri = r[i] - a * Ap[i];
+    r[i] = ri;
+    z[i] = dinv[i] * ri;
+  }
+}
+// 27-point vector stencil on a structured node lattice: vals[(o*3 + a)*n + row], o = (dx+1)+3(dy+1)+9(dz+1)
+__global__ void k_stencil27_spmv(int Nx, int Ny, int Nz, const double *__restrict__ vals, const double *__restrict__ x,
+                                 double *__restrict__ y) {
+  const size_t n = (size_t)3 * Nx * Ny * Nz;
+  GRID_STRIDE(row, n) {
+    const int node = (int)(row / 3);
+    const int i = node % Nx, j = (node / Nx) % Ny, k = node / (Nx * Ny);
+    double s = 0;
+    for (int dz = -1; dz <= 1; dz++) {
+      if (k + dz < 0 || k + dz >= Nz) continue;
+      for (int dy = -1; dy <= 1; dy++) {
+        if (j + dy < 0 || j + dy >= Ny) continue;
+        for (int dx = -1; dx <= 1; dx++) {
+          if (i + dx < 0 || i + dx >= Nx) continue;
+          const int o = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1);
+          const size_t col = (size_t)3 * (node + dx + Nx * (dy + Ny * dz));
+#pragma unroll
+          for (int a = 0; a < 3; a++) s += vals[(size_t)(o * 3 + a) * n + row] * x[col + a];
+        }
+      }
+    }
+    y[row] = s;
+  }
+}
 // ELL sparse mat-vec (slot-major storage): y[r] = sum_s vals[s*n + r] * x[cols[s*n + r]], cols < 0 = empty
 __global__ void k_ell_spmv(size_t n, int nslots, const int *__restrict__ cols, const double *__restrict__ vals,
                            const double *__restrict__ x, double *__restrict__ y) {
@@ -207,6 +251,20 @@ int b200_gather(double *dst, const double *src, const int *idx, size_t n) { VEC_
 int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_set<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
 int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_add<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
 int b200_gather_or_zero(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_gather_or_zero<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
+int b200_vec_axpy_dev(double *y, const double *x, size_t n, const double *num, const double *den, double sign) {
+  VEC_KERNEL((k_axpy_dev<<<grid_for(n, 256), 256, 0, g_stream>>>(y, x, n, num, den, sign)), n);
+}
+int b200_vec_aypx_dev(double *y, const double *x, size_t n, const double *num, const double *den) {
+  VEC_KERNEL((k_aypx_dev<<<grid_for(n, 256), 256, 0, g_stream>>>(y, x, n, num, den)), n);
+}
+int b200_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv, size_t n,
+                    const double *rz, const double *pAp) {
+  VEC_KERNEL((k_pcg_update<<<grid_for(n, 256), 256, 0, g_stream>>>(x, r, z, p, Ap, dinv, n, rz, pAp)), n);
+}
+int b200_stencil27_spmv(int Nx, int Ny, int Nz, const double *vals, const double *x, double *y) {
+  const size_t n = (size_t)3 * Nx * Ny * Nz;
+  VEC_KERNEL((k_stencil27_spmv<<<grid_for(n, 128), 128, 0, g_stream>>>(Nx, Ny, Nz, vals, x, y)), n);
+}
 int b200_ell_spmv(size_t n, int nslots, const int *cols, const double *vals, const double *x, double *y) {
   VEC_KERNEL((k_ell_spmv<<<grid_for(n, 128), 128, 0, g_stream>>>(n, nslots, cols, vals, x, y)), n);
 }

@@ -138,6 +138,65 @@ def pcg(V, A, b, x, M=None, rtol=1e-10, atol=1e-50, maxit=10000, work=None, hist
     return maxit, "maxit", math.sqrt(abs(rz))
 
 
+def jacobi_pcg_nosync(V, A, dinv, b, x, work, rtol, maxit, check_every=10):
+    """Jacobi-preconditioned CG from a zero initial guess whose scalars (r.z, p.Ap) stay on the DEVICE:
+    the loop enqueues kernels without waiting for them and looks at the residual norm only every
+    `check_every` iterations (one host sync per check instead of two per iteration).  Used for the
+    coarse-level solve, where an iteration is a few microseconds of device work.  Same arithmetic on
+    CPU tensors (oracle runs), so iteration counts agree between the two.  Returns iterations run."""
+    r, z, p, Ap = work
+    dev = b.device
+    if not hasattr(V, "_sc") or V._sc.device != dev:
+        V._sc = torch.zeros(4, dtype=torch.float64, device=dev)  # [rz_a, rz_b, pAp, spare]
+    sc = V._sc
+    multi = V.dist is not None and V.dist.get_world_size() > 1
+
+    def ddot(a_, b_, slot):
+        out = sc[slot:slot + 1]
+        if a_.is_cuda:
+            b2(lib.b200_vec_dot(a_.data_ptr(), b_.data_ptr(), a_.numel(), out.data_ptr()))
+        else:
+            out.copy_(torch.dot(a_, b_).reshape(1))
+        if multi:
+            V.dist.all_reduce(out)
+        return out
+
+    x.zero_()
+    V.copy(r, b)
+    V.pmult(z, dinv, r)
+    V.copy(p, z)
+    cur, nxt = 0, 1
+    ddot(r, z, cur)
+    r0 = math.sqrt(abs(float(sc[cur].item())))
+    if r0 == 0.0:
+        return 0
+    it = 0
+    while it < maxit:
+        for _ in range(check_every):
+            A(p, Ap)
+            ddot(p, Ap, 2)
+            if x.is_cuda:
+                b2(lib.b200_pcg_update(x.data_ptr(), r.data_ptr(), z.data_ptr(), p.data_ptr(), Ap.data_ptr(),
+                                       dinv.data_ptr(), x.numel(), sc[cur:cur + 1].data_ptr(), sc[2:3].data_ptr()))
+            else:
+                a = sc[cur] / sc[2]
+                x.add_(p, alpha=float(a))
+                r.add_(Ap, alpha=-float(a))
+                torch.mul(dinv, r, out=z)
+            ddot(r, z, nxt)
+            if p.is_cuda:
+                b2(lib.b200_vec_aypx_dev(p.data_ptr(), z.data_ptr(), p.numel(), sc[nxt:nxt + 1].data_ptr(),
+                                         sc[cur:cur + 1].data_ptr()))
+            else:
+                p.mul_(float(sc[nxt] / sc[cur])).add_(z)
+            cur, nxt = nxt, cur
+            it += 1
+        rn = math.sqrt(abs(float(sc[cur].item())))  # the only host sync of this block of iterations
+        if not math.isfinite(rn) or rn <= rtol * r0:
+            break
+    return it
+
+
 def estimate_lambda_max(V, A, dinv, n, device, its=10, seed=0):
     """Largest eigenvalue of D^-1 A from `its` CG (Lanczos) steps with a deterministic rhs
     (KSPChebyshevEstEigSet + noisy rhs, elasticity.c:540-545; PETSc's PRNG is not reproducible here)."""
@@ -258,22 +317,41 @@ class ColoredCoarseMatrix:
                 self.seeds.append(torch.from_numpy((seed_nodes * 3 + a).astype(np.int64)).to(dev))
         self.Xloc = torch.zeros(n, dtype=torch.float64, device=dev)
         self.Yloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._build_stencil_map()
 
     def assemble(self):
-        """81 local operator applies (ApplyJacobianCoarse_Ceed without the halo: A_loc itself)."""
+        """81 local operator applies (ApplyJacobianCoarse_Ceed without the halo: A_loc itself), then the
+        colour slots are re-indexed by neighbour offset: a 27-point block stencil on the node lattice."""
         for s in range(81):
             self.x.zero_()
             self.x[self.seeds[s]] = 1.0
             self.local_apply(self.x, self.y)
             self.vals[s].copy_(self.y)
         self.vals.mul_((self.cols >= 0).to(torch.float64))
+        torch.gather(self.vals, 0, self.stencil_src, out=self.svals)
+
+    def _build_stencil_map(self):
+        """svals[(o*3 + a)][row] = vals[colour(node + d_o)*3 + a][row], o = (dx+1) + 3(dy+1) + 9(dz+1)."""
+        N, n = self.N, self.dm.lsize
+        i, j, k = self.ijk
+        src = np.zeros((81, n), dtype=np.int64)
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    o = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)
+                    color = ((i + dx) % 3) + 3 * ((j + dy) % 3) + 9 * ((k + dz) % 3)  # colour of the neighbour node
+                    for a in range(3):
+                        src[o * 3 + a] = np.repeat(color * 3 + a, 3)
+        # neighbours outside the lattice point at slots whose value is already zero (masked in assemble)
+        self.stencil_src = torch.from_numpy(src).to(self.dm.device)
+        self.svals = torch.zeros((81, n), dtype=torch.float64, device=self.dm.device)
 
     def mult(self, X, Y):
         dm = self.dm
         dm.zero_and_global_to_local(X, self.Xloc)
         if self.Xloc.is_cuda:
-            b2(lib.b200_ell_spmv(dm.lsize, 81, self.cols.data_ptr(), self.vals.data_ptr(), self.Xloc.data_ptr(),
-                                 self.Yloc.data_ptr()))
+            b2(lib.b200_stencil27_spmv(self.N[0], self.N[1], self.N[2], self.svals.data_ptr(), self.Xloc.data_ptr(),
+                                       self.Yloc.data_ptr()))
         else:
             c = self.cols.long().clamp_min(0)
             self.Yloc.copy_((self.vals * self.Xloc[c] * (self.cols >= 0)).sum(0))
@@ -317,10 +395,8 @@ class PMultigrid:
         self.cdinv.copy_(1.0 / self.diag[0])
 
     def _coarse_solve(self, b, x):
-        V = self.V
-        x.zero_()
-        its, _, _ = pcg(V, self.coarse.mult, b, x, M=lambda r, z: V.pmult(z, self.cdinv, r), rtol=self.coarse_rtol,
-                        maxit=self.coarse_maxit, work=self.cwork)
+        its = jacobi_pcg_nosync(self.V, self.coarse.mult, self.cdinv, b, x, self.cwork, self.coarse_rtol,
+                                self.coarse_maxit)
         self.coarse_its += its
         self.coarse_solves += 1
 

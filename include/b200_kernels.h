@@ -88,6 +88,16 @@ int b200_mask_zero(double *d, const int *idx, size_t n);                        
 /* VecZeroEntries(Xloc) + DMGlobalToLocal(INSERT) in one pass (matops.c:106,33):
  * dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (idx = local dof -> global dof, -1 for ghost / Dirichlet dofs) */
 int b200_gather_or_zero(double *dst, const double *src, const int *idx, size_t n);
+/* BLAS-1 with DEVICE scalars (alpha = sign * num[0] / den[0]) and a fused CG update
+ *   x += alpha p,  r -= alpha Ap,  z = dinv .* r   (alpha = rz[0] / pAp[0])
+ * so that a Krylov loop (the coarse-level solve) runs without a host synchronisation per dot product */
+int b200_vec_axpy_dev(double *y, const double *x, size_t n, const double *num, const double *den, double sign);
+int b200_vec_aypx_dev(double *y, const double *x, size_t n, const double *num, const double *den);
+int b200_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv, size_t n,
+                    const double *rz, const double *pAp);
+/* assembled coarse operator on a structured (Nx,Ny,Nz) node lattice, 3 dofs per node, as a 27-point block
+ * stencil: vals[((dx+1)+3(dy+1)+9(dz+1))*3 + a][row]; y = A x */
+int b200_stencil27_spmv(int Nx, int Ny, int Nz, const double *vals, const double *x, double *y);
 /* assembled coarse-level operator (FormJacobian by colouring, src/misc.c:151-183) in slot-major ELL:
  * y[r] = sum_s vals[s*n + r] * x[cols[s*n + r]]   (cols < 0 = empty slot) */
 int b200_ell_spmv(size_t n, int nslots, const int *cols, const double *vals, const double *x, double *y);
