@@ -200,8 +200,15 @@ def jacobi_pcg_nosync(V, A, dinv, b, x, work, rtol, maxit, check_every=10):
 def estimate_lambda_max(V, A, dinv, n, device, its=10, seed=0):
     """Largest eigenvalue of D^-1 A from `its` CG (Lanczos) steps with a deterministic rhs
     (KSPChebyshevEstEigSet + noisy rhs, elasticity.c:540-545; PETSc's PRNG is not reproducible here)."""
-    g = torch.Generator().manual_seed(1234 + seed)
-    b = torch.rand(n, dtype=torch.float64, generator=g).to(device) - 0.5
+    # deterministic "noisy" rhs generated ON the device with exact integer arithmetic (identical on CPU
+    # and GPU): a multiplicative hash of the dof index, two xorshift-multiply rounds, mapped to [-0.5, 0.5)
+    h = torch.arange(n, dtype=torch.int64, device=device)
+    h = (h * 2654435761 + 1234567 * (seed + 1)) & 0xFFFFFFFF
+    h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
+    h = ((h ^ (h >> 13)) * 3266489917) & 0xFFFFFFFF
+    h = h ^ (h >> 16)
+    b = h.to(torch.float64) / 4294967296.0 - 0.5
+    del h
     x = torch.zeros_like(b)
     r, z, p, Ap = (torch.zeros_like(b) for _ in range(4))
     V.copy(r, b)
