@@ -112,8 +112,10 @@ struct QFArgs {
 };
 
 // Q-vectors are [elem][size][nq]; thread per (elem, q)
-__global__ void k_qfunction(int qf, const __grid_constant__ Material mt, int isize, int nelem, int nq,
-                            const __grid_constant__ QFArgs a) {
+struct QFCtx { double v[4]; };
+
+__global__ void k_qfunction(int qf, const __grid_constant__ Material mt, const __grid_constant__ QFCtx cx, int isize,
+                            int nelem, int nq, const __grid_constant__ QFArgs a) {
   const size_t total = (size_t)nelem * nq;
   GRID_STRIDE(i, total) {
     const size_t e = i / nq, q = i % nq;
@@ -141,6 +143,34 @@ __global__ void k_qfunction(int qf, const __grid_constant__ Material mt, int isi
       OUT(0, 10, 0) = IN(1, 1, 0) * detJ;
       for (int r = 0; r < 3; r++)
         for (int s = 0; s < 3; s++) OUT(0, 10, 1 + 3 * r + s) = Ad[r][s] / detJ;
+      continue;
+    }
+    if (qf == B200_QF_CONST_FORCE) {  // qfunctions/constantForce.h:39-70: force = vector * w detJ
+      const double w = IN(1, 10, 0);
+      for (int c = 0; c < 3; c++) OUT(0, 3, c) = cx.v[c] * w;
+      continue;
+    }
+    if (qf == B200_QF_MMS_FORCE || qf == B200_QF_MMS_TRUE) {
+      // manufactured solution u = (e^2x sin3y cos4z, e^3y sin4z cos2x, e^4z sin2x cos3y) / 1e8
+      // (qfunctions/manufacturedTrue.h:30-56); forcing f = -div sigma(u) for the reference's
+      // linear-elastic stress law (linElas.h:127-139, shear entries mu*e_ij) times w detJ
+      // (qfunctions/manufacturedForce.h:39-103), written from the closed-form second derivatives
+      const double x = IN(0, 3, 0), y = IN(0, 3, 1), z = IN(0, 3, 2);
+      const double ex = exp(2 * x), ey = exp(3 * y), ez = exp(4 * z);
+      const double s2x = sin(2 * x), c2x = cos(2 * x), s3y = sin(3 * y), c3y = cos(3 * y), s4z = sin(4 * z), c4z = cos(4 * z);
+      const double u1 = ex * s3y * c4z, u2 = ey * s4z * c2x, u3 = ez * s2x * c3y;
+      if (qf == B200_QF_MMS_TRUE) {
+        OUT(0, 3, 0) = u1 / 1e8; OUT(0, 3, 1) = u2 / 1e8; OUT(0, 3, 2) = u3 / 1e8;
+        continue;
+      }
+      const double lam = mt.E * mt.nu / ((1 + mt.nu) * (1 - 2 * mt.nu)), mu = mt.mu;
+      const double u1xx = 4 * u1, u1yy = -9 * u1, u1zz = -16 * u1, u1xy = 6 * ex * c3y * c4z, u1xz = -8 * ex * s3y * s4z;
+      const double u2yy = 9 * u2, u2xx = -4 * u2, u2zz = -16 * u2, u2xy = -6 * ey * s4z * s2x, u2yz = 12 * ey * c4z * c2x;
+      const double u3zz = 16 * u3, u3xx = -4 * u3, u3yy = -9 * u3, u3xz = 8 * ez * c2x * c3y, u3yz = -12 * ez * s2x * s3y;
+      const double w = IN(1, 10, 0) / 1e8;
+      OUT(0, 3, 0) = -(lam * (u1xx + u2xy + u3xz) + 2 * mu * u1xx + 0.5 * mu * (u1yy + u2xy + u1zz + u3xz)) * w;
+      OUT(0, 3, 1) = -(lam * (u1xy + u2yy + u3yz) + 2 * mu * u2yy + 0.5 * mu * (u2xx + u1xy + u2zz + u3yz)) * w;
+      OUT(0, 3, 2) = -(lam * (u1xz + u2yz + u3zz) + 2 * mu * u3zz + 0.5 * mu * (u3xx + u1xz + u3yy + u2yz)) * w;
       continue;
     }
     // solid-mechanics point functions: in0 = du [d][c], in1 = qdata[10], (in2 = gradu [c][k])
@@ -252,22 +282,26 @@ extern "C" int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double
   return 0;
 }
 
-extern "C" int b200_qfunction_apply(int qf_id, const b200_physics *phys, int identity_size, int nelem, int nq, int nin,
-                                    const double *const *d_in, int nout, double *const *d_out) {
+extern "C" int b200_qfunction_apply(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
+                                    int nin, const double *const *d_in, int nout, double *const *d_out) {
   if (nin > 4 || nout > 4) return set_error_msg("b200_qfunction_apply: at most 4 input and 4 output fields");
-  const int need_in = qf_id == B200_QF_IDENTITY ? 1 : (qf_id == B200_QF_HYPERSS_DF || qf_id == B200_QF_HYPERFS_DF) ? 3 : 2;
+  if (qf_id <= B200_QF_NONE || qf_id > B200_QF_MMS_TRUE) return set_error_msg("b200_qfunction_apply: unknown QFunction id");
+  const int need_in = (qf_id == B200_QF_IDENTITY || qf_id == B200_QF_MMS_TRUE) ? 1
+                      : (qf_id == B200_QF_HYPERSS_DF || qf_id == B200_QF_HYPERFS_DF) ? 3 : 2;
   const int need_out = (qf_id == B200_QF_HYPERSS_F || qf_id == B200_QF_HYPERFS_F) ? 2 : 1;
-  if (qf_id <= B200_QF_NONE || qf_id > B200_QF_IDENTITY) return set_error_msg("b200_qfunction_apply: unknown QFunction id");
   if (nin < need_in || nout < need_out) return set_error_msg("b200_qfunction_apply: field count does not match the QFunction");
   QFArgs a;
   memset(&a, 0, sizeof a);
   for (int i = 0; i < nin; i++) a.in[i] = d_in[i];
   for (int i = 0; i < nout; i++) a.out[i] = d_out[i];
-  b200_physics dflt = {0.3, 1.0};
-  const Material mt = make_material(phys ? phys : &dflt);
+  QFCtx cx;
+  for (int i = 0; i < 4; i++) cx.v[i] = (h_ctx && i < nctx) ? h_ctx[i] : 0.0;
+  b200_physics ph = {0.3, 1.0};
+  if (h_ctx && nctx >= 2) { ph.nu = h_ctx[0]; ph.E = h_ctx[1]; }
+  const Material mt = make_material(&ph);
   const size_t total = (size_t)nelem * nq;
   if (!total) return 0;
-  k_qfunction<<<grid_for(total, 128), 128, 0, g_stream>>>(qf_id, mt, identity_size, nelem, nq, a);
+  k_qfunction<<<grid_for(total, 128), 128, 0, g_stream>>>(qf_id, mt, cx, identity_size, nelem, nq, a);
   B200_LAUNCH_CHECK("k_qfunction");
   return 0;
 }

@@ -680,7 +680,8 @@ static int qf_lookup(const char *name) {
   static const struct { const char *n; int id; } table[] = {
       {"SetupGeo", B200_QF_SETUPGEO},     {"LinElasF", B200_QF_LINELAS_F},   {"LinElasdF", B200_QF_LINELAS_DF},
       {"HyperSSF", B200_QF_HYPERSS_F},    {"HyperSSdF", B200_QF_HYPERSS_DF}, {"HyperFSF", B200_QF_HYPERFS_F},
-      {"HyperFSdF", B200_QF_HYPERFS_DF},  {"Identity", B200_QF_IDENTITY},    {NULL, 0}};
+      {"HyperFSdF", B200_QF_HYPERFS_DF},  {"Identity", B200_QF_IDENTITY},    {"SetupConstantForce", B200_QF_CONST_FORCE},
+      {"SetupMMSForce", B200_QF_MMS_FORCE}, {"MMSTrueSoln", B200_QF_MMS_TRUE}, {NULL, 0}};
   for (int i = 0; table[i].n; i++)
     if (!strcmp(table[i].n, name)) return table[i].id;
   return B200_QF_NONE;
@@ -974,10 +975,19 @@ static int op_run_qfunction(CeedOperator op, CeedInt nelem, CeedInt nq, const do
     CeedChk(grow(ceed, &op->qbuf[MAXF + i], &op->qbytes[MAXF + i], qsz));
     qout[i] = op->qbuf[MAXF + i];
   }
-  b200_physics phys = {0.3, 1.0};
+  /* context: read through the caller's host pointer at apply time, whatever ctxsize says
+     (Physics {nu, E}: 2 doubles; constant forcing vector: 3 doubles, declared as sizeof(double),
+     setuplibceed.c:566-567) */
+  double hctx[4] = {0, 0, 0, 0};
+  int nctx = 0;
   const int id = qf->qf_id;
-  if (id != B200_QF_SETUPGEO && id != B200_QF_IDENTITY) CeedChk(qf_physics(qf, &phys));
-  B2(ceed, b200_qfunction_apply(id, &phys, qf->identity_size, nelem, nq, qf->nin, qin, qf->nout, qout));
+  if (id == B200_QF_CONST_FORCE) nctx = 3;
+  else if (id != B200_QF_SETUPGEO && id != B200_QF_IDENTITY && id != B200_QF_MMS_TRUE) nctx = 2;
+  if (nctx) {
+    if (!qf->ctx) return CeedError(ceed, 1, "QFunction %s needs a context (CeedQFunctionSetContext)", qf->name);
+    memcpy(hctx, qf->ctx, sizeof(double) * nctx);
+  }
+  B2(ceed, b200_qfunction_apply(id, hctx, nctx, qf->identity_size, nelem, nq, qf->nin, qin, qf->nout, qout));
   return 0;
 }
 

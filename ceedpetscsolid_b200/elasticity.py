@@ -18,6 +18,16 @@ from . import matops, setuplibceed, solver
 from .mesh import BoxMesh, grid_for
 
 
+def bc_mms(coords, load):
+    """BCMMS (src/boundary.c:31-45): the manufactured solution on the boundary."""
+    x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+    u = np.empty_like(coords)
+    u[:, 0] = np.exp(2 * x) * np.sin(3 * y) * np.cos(4 * z) / 1e8 * load
+    u[:, 1] = np.exp(3 * y) * np.sin(4 * z) * np.cos(2 * x) / 1e8 * load
+    u[:, 2] = np.exp(4 * z) * np.sin(2 * x) * np.cos(3 * y) / 1e8 * load
+    return u
+
+
 def bc_clamp(coords, load, clamp):
     """BCClamp (src/boundary.c:53-74): clamp = [tx,ty,tz, kx,ky,kz, theta/pi] (translate, axis, rotation)."""
     x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
@@ -44,6 +54,9 @@ class AppCtx:
     multigrid: str = "logarithmic"
     num_steps: int = 10
     perturb: float = 0.0
+    forcing: str = "none"          # -forcing none|constant|mms
+    forcing_vector: tuple = (0.0, -1.0, 0.0)
+    test_mode: bool = False        # -test: MMS forcing, BCMMS on every boundary face (cloptions.c:185-187, setupdm.c:160-170)
     # clamped faces: (axis, side) -> [tx,ty,tz, kx,ky,kz, theta/pi]  (-bc_clamp, -bc_clamp_N_translate/_rotate)
     clamp: dict = field(default_factory=lambda: {(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
 
@@ -70,8 +83,13 @@ class GpuLevel:
         u.Yceed.take_array(u.memType)
 
     def residual(self, U, F, load):
+        """FormResidual_Ceed minus the (load-scaled) forcing vector: SNESSolve(snes, F_ext, U) (elasticity.c:645-654)."""
         self.res_user.loadIncrement = load
         matops.FormResidual_Ceed(U, F, self.res_user)
+        if self.forcing is not None:
+            solver.Vec.axpy(F, -load, self.forcing)
+
+    forcing = None
 
     def bc_increment_rhs(self, F, load_prev, load):
         """F = P^T A_loc(U) [0; u_bc(load) - u_bc(load_prev)]: the Jacobian applied to the boundary increment."""
@@ -80,6 +98,8 @@ class GpuLevel:
         u.dm.insert_boundary_values(u.Xloc, r.bc_values(load) - r.bc_values(load_prev))
         self.local_apply(u.Xloc, u.Yloc)
         u.dm.local_to_global(u.Yloc, F)
+        if self.forcing is not None:
+            solver.Vec.axpy(F, -(load - load_prev), self.forcing)
 
 
 class GpuTransfer:
@@ -104,7 +124,9 @@ class Elasticity:
         self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}")
         self.degrees, self.data, self.phys = setuplibceed.setup_all(self.ceed, self.mesh, app.problem, app.degree, app.nu,
                                                                     app.E, app.qextra, app.multigrid)
-        faces = list(app.clamp.keys())
+        if app.test_mode:
+            app.forcing = "mms"
+        faces = "all" if app.test_mode else list(app.clamp.keys())
         self.dms, self.users = [], []
         for l, deg in enumerate(self.degrees):
             halo = None
@@ -127,6 +149,17 @@ class Elasticity:
             pr = matops.setup_prolong_restrict_ctx(self.dms[l - 1], self.dms[l], self.ceed, self.data[l - 1], self.data[l],
                                                    self.users[l - 1], self.users[l])
             self.transfers.append(GpuTransfer(pr))
+        if app.forcing != "none":
+            # global forcing vector (elasticity.c:236-245, 288-300): L-vector from the forcing operator, then L2G ADD
+            floc = self.dms[fine].create_local_vector()
+            fc = self.ceed.Vector(floc.numel())
+            fc.set_array(floc)
+            setuplibceed.setup_forcing(self.ceed, self.mesh, self.data[fine], app.forcing, self.phys, app.forcing_vector, fc)
+            fc.take_array()
+            fc.destroy()
+            Fext = self.dms[fine].create_global_vector()
+            self.dms[fine].local_to_global(floc, Fext)
+            self.levels[fine].forcing = Fext
         self.V = solver.Vec(dist if world > 1 else None)
         self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol)
         self.U = self.dms[fine].create_global_vector()
@@ -138,6 +171,8 @@ class Elasticity:
         coords = dm.mesh.node_coords(p)
         bc_nodes = np.flatnonzero(dm.bc_nodes)
         xyz = coords[bc_nodes]
+        if app.test_mode:
+            return lambda load: torch.from_numpy(bc_mms(xyz, load).reshape(-1)).to(dm.device)
         face_of = np.full(bc_nodes.size, -1)
         for fi, (axis, side) in enumerate(app.clamp.keys()):  # later faces win on shared edges, as DMAddBoundary order
             on = dm.mesh.boundary_mask(p, [(axis, side)])[bc_nodes]
@@ -162,6 +197,15 @@ class Elasticity:
         # "DoFs/Sec in SNES" = global dofs x total KSP iterations / solve time (elasticity.c:762-764), in MDoF/s
         out["mdofs_per_sec_in_snes"] = 1e-6 * out["dofs_global_unconstrained"] * out["ksp_its"] / max(out["time_s"], 1e-12)
         return out
+
+    def mms_l2_error(self):
+        """elasticity.c:770-816: |U - U_true| / |U| over the global (unconstrained) dofs."""
+        fine = len(self.degrees) - 1
+        true_l = setuplibceed.setup_true_solution(self.ceed, self.mesh, self.data[fine], self.degrees[fine] + 1)
+        dm = self.dms[fine]
+        tg = torch.from_numpy(true_l).to(dm.device)[dm.free_owned_idx.long()]
+        err2, u2 = self.V.dot(self.U - tg, self.U - tg), self.V.dot(self.U, self.U)
+        return math.sqrt(err2 / u2)
 
     def _global_unconstrained(self):
         n = torch.tensor([self.dms[-1].nglobal], dtype=torch.float64, device=self.dms[-1].device)

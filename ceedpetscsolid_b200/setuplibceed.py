@@ -127,6 +127,58 @@ def setup_fine_level(ceed, mesh, problem, degree, phys, data, qextra=0, node_per
     return d
 
 
+FORCING_OPTIONS = {  # forcingOptions[] (setuplibceed.c:110-125)
+    "constant": "qfunctions/constantForce.h:SetupConstantForce",
+    "mms": "qfunctions/manufacturedForce.h:SetupMMSForce",
+}
+
+
+def setup_forcing(ceed, mesh, data, forcing, phys, forcing_vector, force_ceed):
+    """Forcing term (setuplibceed.c:550-584): force_L = E^T B^T f(B x, qdata)."""
+    import ctypes as C
+    d = data
+    qf = ceed.QFunction(1, FORCING_OPTIONS[forcing])
+    qf.add_input("x", 3, EVAL_INTERP)
+    qf.add_input("qdata", 10, EVAL_NONE)
+    qf.add_output("force", 3, EVAL_INTERP)
+    if forcing == "mms":
+        qf.set_context(phys)
+    else:
+        fv = (C.c_double * 3)(*forcing_vector)
+        qf.set_context(fv, size=8)  # sizeof(*appCtx->forcingVector), setuplibceed.c:566-567
+    xcoord = d.Erestrictx.create_vector()
+    xcoord.set_array(mesh.coord_lvector(), libceed.MEM_HOST, libceed.COPY_VALUES)
+    op = ceed.Operator(qf)
+    op.set_field("x", d.Erestrictx, d.basisx, VECTOR_ACTIVE)
+    op.set_field("qdata", d.Erestrictqdi, BASIS_COLLOCATED, d.qdata)
+    op.set_field("force", d.Erestrictu, d.basisu, VECTOR_ACTIVE)
+    op.apply(xcoord, force_ceed)
+    op.destroy(); qf.destroy(); xcoord.destroy()
+
+
+def setup_true_solution(ceed, mesh, data, P):
+    """MMS true solution at the mesh nodes (setuplibceed.c:592-643), multiplicity-corrected."""
+    d = data
+    basisxtrue = ceed.BasisTensorH1Lagrange(3, 3, 2, P, GAUSS_LOBATTO)
+    qf = ceed.QFunction(1, "qfunctions/manufacturedTrue.h:MMSTrueSoln")
+    qf.add_input("x", 3, EVAL_INTERP)
+    qf.add_output("true_soln", 3, EVAL_NONE)
+    op = ceed.Operator(qf)
+    op.set_field("x", d.Erestrictx, basisxtrue, VECTOR_ACTIVE)
+    op.set_field("true_soln", d.Erestrictu, BASIS_COLLOCATED, VECTOR_ACTIVE)
+    xcoord = d.Erestrictx.create_vector()
+    xcoord.set_array(mesh.coord_lvector(), libceed.MEM_HOST, libceed.COPY_VALUES)
+    truesoln = d.Erestrictu.create_vector()
+    op.apply(xcoord, truesoln)
+    mult = d.Erestrictu.create_vector()
+    mult.set_value(0.0)
+    d.Erestrictu.get_multiplicity(mult)
+    out = truesoln.to_numpy() / mult.to_numpy()
+    for o in (op, qf, basisxtrue, xcoord, truesoln, mult):
+        o.destroy()
+    return out
+
+
 def setup_level(ceed, mesh, problem, degrees, level, phys, data, qextra=0, node_perm=None, multigrid=True):
     """SetupLibceedLevel (setuplibceed.c:748-863): data = list of CeedData, fine level last."""
     opt = PROBLEM_OPTIONS[problem]

@@ -37,7 +37,10 @@ enum {
   B200_QF_HYPERSS_DF,  /* qfunctions/hyperSS.h:187 */
   B200_QF_HYPERFS_F,   /* qfunctions/hyperFS.h:147 */
   B200_QF_HYPERFS_DF,  /* qfunctions/hyperFS.h:286 */
-  B200_QF_IDENTITY     /* libCEED gallery "Identity" */
+  B200_QF_IDENTITY,    /* libCEED gallery "Identity" */
+  B200_QF_CONST_FORCE, /* qfunctions/constantForce.h:39   SetupConstantForce */
+  B200_QF_MMS_FORCE,   /* qfunctions/manufacturedForce.h:39 SetupMMSForce    */
+  B200_QF_MMS_TRUE     /* qfunctions/manufacturedTrue.h:30  MMSTrueSoln      */
 };
 
 /* Physics_private {nu, E}  /root/reference/elasticity.h:30-37 */
@@ -133,8 +136,10 @@ int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double *d_interp1
                      const double *d_u, double *d_v);
 
 /* ---- generic path: CeedQFunctionApply for recognised QFunctions (App. B.4) ---------- */
-/* in[k] / out[k]: device Q-vectors [elem][size_k][nq] in field declaration order */
-int b200_qfunction_apply(int qf_id, const b200_physics *phys, int identity_size, int nelem, int nq,
+/* in[k] / out[k]: device Q-vectors [elem][size_k][nq] in field declaration order.
+ * h_ctx: the QFunction context as HOST doubles ({nu, E} for the material models and the MMS forcing,
+ * the 3-vector for the constant forcing; may be NULL when the QFunction takes none) */
+int b200_qfunction_apply(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
                          int nin, const double *const *d_in, int nout, double *const *d_out);
 
 /* generic-path piece of CeedOperatorLinearAssembleDiagonal (App. B.5): one unit-input pass,

@@ -325,3 +325,46 @@ int port_HyperFSdF(void *ctx, int Q, const double *const *in, double *const *out
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------- forcing / MMS */
+/* SetupConstantForce, qfunctions/constantForce.h:39-70: in = {x[3] (unused), qdata[10]}, ctx = vector[3] */
+int port_SetupConstantForce(void *ctx, int Q, const double *const *in, double *const *out) {
+  const double *v = (const double *)ctx, *qd = in[1];
+  for (int i = 0; i < Q; i++)
+    for (int c = 0; c < 3; c++) out[0][c * Q + i] = v[c] * qd[i];
+  return 0;
+}
+
+/* manufactured solution u = (e^2x sin3y cos4z, e^3y sin4z cos2x, e^4z sin2x cos3y) / 1e8,
+ * qfunctions/manufacturedTrue.h:30-56 */
+int port_MMSTrueSoln(void *ctx, int Q, const double *const *in, double *const *out) {
+  (void)ctx;
+  for (int i = 0; i < Q; i++) {
+    const double x = in[0][i], y = in[0][Q + i], z = in[0][2 * Q + i];
+    out[0][i] = exp(2 * x) * sin(3 * y) * cos(4 * z) / 1e8;
+    out[0][Q + i] = exp(3 * y) * sin(4 * z) * cos(2 * x) / 1e8;
+    out[0][2 * Q + i] = exp(4 * z) * sin(2 * x) * cos(3 * y) / 1e8;
+  }
+  return 0;
+}
+
+/* SetupMMSForce, qfunctions/manufacturedForce.h:39-103, restated from the mathematics:
+ * f = -div sigma(u) * w detJ with the reference's linear-elastic stress law (linElas.h:127-139,
+ * sigma_ii = lambda tr(e) + 2 mu e_ii, sigma_ij = mu e_ij) and the closed-form second derivatives of u. */
+int port_SetupMMSForce(void *ctx, int Q, const double *const *in, double *const *out) {
+  const PortPhysics *p = (const PortPhysics *)ctx;
+  const double lam = p->E * p->nu / ((1 + p->nu) * (1 - 2 * p->nu)), mu = p->E / (2 * (1 + p->nu));
+  for (int i = 0; i < Q; i++) {
+    const double x = in[0][i], y = in[0][Q + i], z = in[0][2 * Q + i], w = in[1][i] / 1e8;
+    const double ex = exp(2 * x), ey = exp(3 * y), ez = exp(4 * z);
+    const double s2x = sin(2 * x), c2x = cos(2 * x), s3y = sin(3 * y), c3y = cos(3 * y), s4z = sin(4 * z), c4z = cos(4 * z);
+    const double u1 = ex * s3y * c4z, u2 = ey * s4z * c2x, u3 = ez * s2x * c3y;
+    const double u1xx = 4 * u1, u1yy = -9 * u1, u1zz = -16 * u1, u1xy = 6 * ex * c3y * c4z, u1xz = -8 * ex * s3y * s4z;
+    const double u2yy = 9 * u2, u2xx = -4 * u2, u2zz = -16 * u2, u2xy = -6 * ey * s4z * s2x, u2yz = 12 * ey * c4z * c2x;
+    const double u3zz = 16 * u3, u3xx = -4 * u3, u3yy = -9 * u3, u3xz = 8 * ez * c2x * c3y, u3yz = -12 * ez * s2x * s3y;
+    out[0][i] = -(lam * (u1xx + u2xy + u3xz) + 2 * mu * u1xx + 0.5 * mu * (u1yy + u2xy + u1zz + u3xz)) * w;
+    out[0][Q + i] = -(lam * (u1xy + u2yy + u3yz) + 2 * mu * u2yy + 0.5 * mu * (u2xx + u1xy + u2zz + u3yz)) * w;
+    out[0][2 * Q + i] = -(lam * (u1xz + u2yz + u3zz) + 2 * mu * u3zz + 0.5 * mu * (u3xx + u1xz + u3yy + u2yz)) * w;
+  }
+  return 0;
+}

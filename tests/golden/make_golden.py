@@ -55,6 +55,18 @@ def run(which, Q, J, w, ug, dug, nu=0.3, E=1.0):
         f, gradu = oracle.call_qf(name + "F", which, phys, Q, [ug.reshape(9, Q), qd], [9, 9])
         (df,) = oracle.call_qf(name + "dF", which, phys, Q, [dug.reshape(9, Q), qd, gradu], [9])
         out[name + "F"], out[name + "F_gradu"], out[name + "dF"] = f, gradu, df
+    # forcing / manufactured solution: coordinates = the first three rows of J (any numbers will do)
+    xyz = J.reshape(9, Q)[:3] + 0.25
+    (out["SetupMMSForce"],) = oracle.call_qf("SetupMMSForce", which, phys, Q, [xyz, qd], [3])
+    (out["MMSTrueSoln"],) = oracle.call_qf("MMSTrueSoln", which, None, Q, [xyz], [3])
+    fv = (oracle.C.c_double * 3)(0.3, -1.0, 2.5)
+    f = oracle.C.cast(oracle.qf("SetupConstantForce", which), oracle.QFN)
+    inp = (oracle.C.POINTER(oracle.C.c_double) * 2)(xyz.ctypes.data_as(oracle.C.POINTER(oracle.C.c_double)),
+                                                    qd.ctypes.data_as(oracle.C.POINTER(oracle.C.c_double)))
+    o = np.zeros((3, Q))
+    outp = (oracle.C.POINTER(oracle.C.c_double) * 1)(o.ctypes.data_as(oracle.C.POINTER(oracle.C.c_double)))
+    assert f(oracle.C.cast(fv, oracle.C.c_void_p), Q, inp, outp) == 0
+    out["SetupConstantForce"] = o
     return out
 
 

@@ -77,3 +77,60 @@ def test_gpu_and_oracle_agree_on_iteration_counts_and_solution(problem, degree, 
     assert out["ksp_its"] == ref["ksp_its"], (out, ref)
     u = el.U.cpu().numpy()
     assert np.linalg.norm(u - Uref.numpy()) < 1e-9 * np.linalg.norm(Uref.numpy())
+
+
+@pytest.mark.gpu
+def test_reference_acceptance_run_mms(tmp_path):
+    """The reference's only test (elasticity.c:36): `-test -degree 3 -nu 0.3 -E 1 -dm_plex_box_faces 3,3,3`
+    = linElas with the manufactured forcing and BCMMS on the whole boundary; passes iff the relative
+    L2 error against the manufactured solution is at most 5 % (elasticity.c:800-811)."""
+    from ceedpetscsolid_b200.elasticity import Elasticity
+    app = AppCtx(problem="linElas", degree=3, n=(3, 3, 3), nu=0.3, E=1.0, num_steps=1, test_mode=True)
+    el = Elasticity(app)
+    out = el.solve()
+    assert out["converged"]
+    err = el.mms_l2_error()
+    assert err < 0.05, err
+    assert err < 5e-3  # what this discretisation actually delivers
+    # finer mesh: the error must drop (degree-3 elements: ~h^4)
+    el2 = Elasticity(AppCtx(problem="linElas", degree=3, n=(6, 6, 6), nu=0.3, E=1.0, num_steps=1, test_mode=True))
+    assert el2.solve()["converged"]
+    err2 = el2.mms_l2_error()
+    assert err2 < err / 8, (err, err2)
+
+
+@pytest.mark.gpu
+def test_forcing_operators_match_the_oracle():
+    """SetupMMSForce / SetupConstantForce through the generic operator path (INTERP in, INTERP^T out)."""
+    import ctypes as C
+    from ceedpetscsolid_b200 import ceed as libceed, setuplibceed
+    from ceedpetscsolid_b200.mesh import BoxMesh
+    from oracle import oracle
+    mesh = BoxMesh(n=(3, 2, 2), perturb=0.1, seed=0)
+    c = libceed.Ceed("/gpu/b200")
+    deg, P, Q = 2, 3, 3
+    phys = libceed.Physics(0.3, 1.0)
+    data = setuplibceed.CeedData()
+    setuplibceed.setup_fine_level(c, mesh, "linElas", deg, phys, data)
+    nel = mesh.nelem
+    Bx, Dx, _, qw = oracle.basis_1d(2, Q, 0)
+    Bu, Du, _, _ = oracle.basis_1d(P, Q, 0)
+    qdata = oracle.setup_geo(nel, Q, mesh.offsets(1), mesh.coord_lvector())
+    xe = mesh.coord_lvector()[mesh.offsets(1)[:, None, :] + np.arange(3)[None, :, None]]
+    xq = oracle.basis_apply(nel, 3, 2, Q, Bx, Dx, qw, 0, 1, xe).reshape(nel, 3, Q ** 3)
+    for forcing, ctx in (("mms", oracle.Physics(0.3, 1.0)), ("constant", (C.c_double * 3)(0.3, -1.0, 2.5))):
+        fq = np.zeros((nel, 3, Q ** 3))
+        for e in range(nel):
+            name = "SetupMMSForce" if forcing == "mms" else "SetupConstantForce"
+            f = C.cast(oracle.qf(name, oracle.default_which()), oracle.QFN)
+            ins = [np.ascontiguousarray(xq[e]), np.ascontiguousarray(qdata[e])]
+            inp = (C.POINTER(C.c_double) * 2)(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in ins])
+            outp = (C.POINTER(C.c_double) * 1)(fq[e].ctypes.data_as(C.POINTER(C.c_double)))
+            assert f(C.cast(C.pointer(ctx), C.c_void_p), Q ** 3, inp, outp) == 0
+        fe = oracle.basis_apply(nel, 3, P, Q, Bu, Du, qw, 1, 1, fq.reshape(nel, -1))
+        ref = np.zeros(mesh.lsize(deg))
+        np.add.at(ref, (mesh.offsets(deg)[:, None, :] + np.arange(3)[None, :, None]).reshape(-1), fe.reshape(-1))
+        fc = c.Vector(mesh.lsize(deg))
+        setuplibceed.setup_forcing(c, mesh, data, forcing, phys, (0.3, -1.0, 2.5), fc)
+        got = fc.to_numpy()
+        assert np.linalg.norm(got - ref) < 1e-12 * np.linalg.norm(ref), forcing
