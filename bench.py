@@ -188,7 +188,7 @@ def main():
                 else f"{problem} degree {p} Jacobian MatMult, box {args.n}^3 sharded")
     config = {"workload": workload, "problem": problem, "degree": p, "levels": "fine level of {1,2,4}",
               "elements_per_gpu": None, "scatter": "fp64 atomics", "l2": "inputs larger than L2 (no flush needed)",
-              "bricks": None}
+              "bricks": None, "halo": "none (1 GPU)" if world == 1 else "NCCL p2p, one sum-and-share exchange per MatMult"}
 
     # ------------------------------------------------------------------ CPU reference arm
     if args.impl == "reference":
@@ -236,7 +236,8 @@ def main():
     if world > 1:
         from ceedpetscsolid_b200.halo import Halo
         halo = Halo(gmesh, grid, rank, p, dist)
-    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo)
+    # N > 1: shared-dof global vectors -> one symmetric sum-and-share halo exchange per MatMult
+    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=True)
     user = matops.setup_jacobian_ctx(dm, ceed, data[fine], phys)
 
     # state: smooth admissible displacement -> residual fills gradu

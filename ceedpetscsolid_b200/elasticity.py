@@ -133,7 +133,7 @@ class Elasticity:
             if world > 1:
                 from .halo import Halo
                 halo = Halo(self.gmesh, grid, rank, deg, dist)
-            dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}")
+            dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}", shared=True)
             self.dms.append(dm)
             self.users.append(matops.setup_jacobian_ctx(dm, self.ceed, self.data[l], self.phys))
         fine = len(self.degrees) - 1
@@ -161,6 +161,11 @@ class Elasticity:
             self.dms[fine].local_to_global(floc, Fext)
             self.levels[fine].forcing = Fext
         self.V = solver.Vec(dist if world > 1 else None)
+        self.V.consistent = {}
+        for dm in self.dms:
+            if dm.dot_weight is not None:
+                self.V.weights[dm.nglobal] = dm.dot_weight
+                self.V.consistent[dm.nglobal] = dm.make_consistent
         self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol)
         self.U = self.dms[fine].create_global_vector()
 
@@ -208,7 +213,9 @@ class Elasticity:
         return math.sqrt(err2 / u2)
 
     def _global_unconstrained(self):
-        n = torch.tensor([self.dms[-1].nglobal], dtype=torch.float64, device=self.dms[-1].device)
+        dm = self.dms[-1]
+        local = float(dm.dot_weight.sum().item()) if dm.dot_weight is not None else float(dm.nglobal)
+        n = torch.tensor([local], dtype=torch.float64, device=dm.device)
         if self.dist is not None and self.dist.get_world_size() > 1:
             self.dist.all_reduce(n)
-        return int(n.item())
+        return int(round(n.item()))

@@ -99,6 +99,14 @@ class Halo:
 
         self.own_cat, self.own_views = layout(self.send_own)
         self.ghost_cat, self.ghost_views = layout(self.recv_ghost)
+        # "sum-and-share": every dof shared with r, both directions at once (same order on both sides)
+        self.shared_all = {r: torch.from_numpy(dofs(shared[r])).to(self.device) for r in self.neighbours}
+        self.share_cat, self.share_views = layout(self.shared_all)
+        # number of ranks holding each local node (1 in the interior)
+        cnt = np.ones(self.nnodes)
+        for r in self.neighbours:
+            cnt[shared[r]] += 1
+        self.rank_multiplicity = cnt
         self._buf = {}
 
     def _buffer(self, key, n, like):
@@ -147,6 +155,12 @@ class Halo:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         self._scatter(vec, recv_cat, rbuf, add)
+
+    def sum_and_share(self, Yloc):
+        """One symmetric exchange replacing ghost->owner ADD followed by owner->ghost INSERT: every rank
+        sends its partial sums on ALL shared dofs to every sharer and adds what it receives, so all copies
+        end up with the assembled value (allowed harness optimisation)."""
+        self._exchange(Yloc, self.share_cat, self.share_views, self.share_cat, self.share_views, add=True, tag="sas")
 
     def owner_to_ghost(self, Xloc):
         """DMGlobalToLocal part 2: ghosts receive the owner's value."""

@@ -28,13 +28,18 @@ class LevelDM:
     or None.  `halo`: a ceedpetscsolid_b200.halo.Halo for partitioned runs, else None.
     """
 
-    def __init__(self, mesh, degree, bc_faces="all", halo=None, device="cuda", node_perm=None):
+    def __init__(self, mesh, degree, bc_faces="all", halo=None, device="cuda", node_perm=None, shared=False):
+        """shared=True (partitioned runs): "global" vectors keep a consistent copy of every interface dof on
+        every rank that holds it, so DMGlobalToLocal needs no communication and DMLocalToGlobal(ADD) is ONE
+        symmetric sum-and-share exchange instead of two one-directional ones; `dot_weight` (1/#ranks holding
+        the dof) makes inner products count each dof once."""
         self.mesh, self.degree, self.halo = mesh, degree, halo
+        self.shared = bool(shared and halo is not None)
         self.device = torch.device(device)
         nn = mesh.num_nodes(degree)
         self.lsize = 3 * nn
         bc_nodes = mesh.boundary_mask(degree, bc_faces) if bc_faces is not None else np.zeros(nn, bool)
-        owned_nodes = halo.owned_node_mask if halo is not None else np.ones(nn, bool)
+        owned_nodes = halo.owned_node_mask if (halo is not None and not self.shared) else np.ones(nn, bool)
         free_owned = (~bc_nodes) & owned_nodes
         if node_perm is not None:  # local numbering is a permutation of the lexicographic one
             fo = np.zeros(nn, bool); fo[node_perm] = free_owned
@@ -48,6 +53,10 @@ class LevelDM:
         l2g = np.full(self.lsize, -1, dtype=np.int32)  # local dof -> global dof (-1: ghost or Dirichlet)
         l2g[fo_idx] = np.arange(fo_idx.size, dtype=np.int32)
         self.local_to_global_idx = torch.from_numpy(l2g).to(self.device)
+        self.dot_weight = None
+        if self.shared:
+            w = np.repeat(1.0 / halo.rank_multiplicity, 3)[fo_idx]
+            self.dot_weight = torch.from_numpy(w).to(self.device)
         self.bc_idx = torch.from_numpy(bc_idx).to(self.device)
         self._fo_host, self._bc_host = fo_idx, bc_idx
 
@@ -68,7 +77,7 @@ class LevelDM:
             b2(lib.b200_scatter_set(Xloc.data_ptr(), self.free_owned_idx.data_ptr(), X.data_ptr(), self.nglobal))
         else:
             Xloc.numpy()[self._fo_host] = X.numpy()
-        if self.halo is not None:
+        if self.halo is not None and not self.shared:
             self.halo.owner_to_ghost(Xloc)
 
     def zero_and_global_to_local(self, X, Xloc):
@@ -76,7 +85,7 @@ class LevelDM:
         pass over Xloc (device vectors); identical result, one third of the memory traffic."""
         if Xloc.is_cuda:
             b2(lib.b200_gather_or_zero(Xloc.data_ptr(), X.data_ptr(), self.local_to_global_idx.data_ptr(), self.lsize))
-            if self.halo is not None:
+            if self.halo is not None and not self.shared:
                 self.halo.owner_to_ghost(Xloc)
         else:
             Xloc.zero_()
@@ -85,11 +94,23 @@ class LevelDM:
     def local_to_global(self, Yloc, Y):
         """VecZeroEntries(Y); DMLocalToGlobal(dm, Yloc, ADD_VALUES, Y): constrained dofs dropped."""
         if self.halo is not None:
-            self.halo.ghost_to_owner_add(Yloc)
+            if self.shared:
+                self.halo.sum_and_share(Yloc)
+            else:
+                self.halo.ghost_to_owner_add(Yloc)
         if Yloc.is_cuda:
             b2(lib.b200_gather(Y.data_ptr(), Yloc.data_ptr(), self.free_owned_idx.data_ptr(), self.nglobal))
         else:
             Y.numpy()[:] = Yloc.numpy()[self._fo_host]
+
+    def make_consistent(self, X):
+        """shared layouts: replace every copy of an interface dof by the average of the copies"""
+        if not self.shared:
+            return
+        Xl = self.create_local_vector(MEM_DEVICE if X.is_cuda else MEM_HOST)
+        X.mul_(self.dot_weight)
+        self.global_to_local(X, Xl)
+        self.local_to_global(Xl, X)
 
     def insert_boundary_values(self, Xloc, values):
         """DMPlexInsertBoundaryValues stand-in: values = tensor over bc dofs (or None = zero)."""
@@ -194,8 +215,11 @@ def setup_prolong_restrict_ctx(dmC, dmF, ceed, dataC, dataF, userC, userF, memTy
     mult_ceed.destroy()
     mult = mult.to(dmF.device) if memType == MEM_DEVICE else mult
     if dmF.halo is not None:
-        dmF.halo.ghost_to_owner_add(mult)
-        dmF.halo.owner_to_ghost(mult)
+        if dmF.shared:
+            dmF.halo.sum_and_share(mult)
+        else:
+            dmF.halo.ghost_to_owner_add(mult)
+            dmF.halo.owner_to_ghost(mult)
     multVec = torch.where(mult > 0, 1.0 / mult, mult)
     return UserMultProlongRestr(dmC=dmC, dmF=dmF, locVecC=userC.Xloc, locVecF=userF.Xloc, multVec=multVec,
                                 ceedVecC=dataC.xceed, ceedVecF=dataF.xceed, opProlong=dataF.opProlong,

