@@ -31,12 +31,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
-ALG_BYTES_PER_ELEM = {  # 8 Q^3 (10 + g) + 4 P^3 + 48 p^3
-    ("hyperFS", 4): 22572, ("hyperSS", 3): 11280, ("linElas", 2): 2652,
-}
-
-
 def alg_bytes(problem, p, qextra=0):
+    """8 Q^3 (10 + g) + 4 P^3 + 48 p^3 bytes per element (22 572 for hyperFS p = 4)."""
     P, Q = p + 1, p + 1 + qextra
     g = 0 if problem == "linElas" else 9
     return 8 * Q ** 3 * (10 + g) + 4 * P ** 3 + 48 * p ** 3
