@@ -133,9 +133,35 @@ def test_standalone_restriction_and_basis_apply(G):
     assert rel_err(lv2.to_numpy(), ref_l) < TOL
 
 
-@pytest.mark.parametrize("problem,p,n", [("hyperSS", 3, 32), ("hyperFS", 4, 64)])
+def test_empty_restriction_and_operator(G):
+    """nelem = 0 (a rank that owns no elements): every call is a no-op, nothing is launched out of bounds."""
+    from ceedpetscsolid_b200 import ceed as libceed
+    c = libceed.Ceed("/gpu/b200")
+    r = c.ElemRestriction(0, 27, 3, 1, 30, np.zeros(0, dtype=np.int32))
+    rq = c.StridedElemRestriction(0, 27, 10, 0)
+    b = c.BasisTensorH1Lagrange(3, 3, 3, 3)
+    qd = c.Vector(0)
+    qf = c.QFunction(1, "qfunctions/linElas.h:LinElasdF")
+    qf.add_input("deltadu", 9, libceed.EVAL_GRAD)
+    qf.add_input("qdata", 10, libceed.EVAL_NONE)
+    qf.add_output("deltadv", 9, libceed.EVAL_GRAD)
+    qf.set_context(libceed.Physics(0.3, 1.0))
+    op = c.Operator(qf)
+    op.set_field("deltadu", r, b, libceed.VECTOR_ACTIVE)
+    op.set_field("qdata", rq, libceed.BASIS_COLLOCATED, qd)
+    op.set_field("deltadv", r, b, libceed.VECTOR_ACTIVE)
+    x, y = c.Vector(30), c.Vector(30)
+    x.set_value(1.0)
+    y.set_value(7.0)
+    op.apply(x, y)
+    np.testing.assert_array_equal(y.to_numpy(), np.zeros(30))  # CeedOperatorApply zeroes its output
+    op.linear_assemble_diagonal(y)
+    np.testing.assert_array_equal(y.to_numpy(), np.zeros(30))
+
+
+@pytest.mark.parametrize("problem,p,n", [("hyperSS", 3, 32), ("hyperFS", 4, 64), ("hyperFS", 4, 80)])
 def test_properties_at_baseline_sizes(G, problem, p, n):
-    """BASELINE configs[1] and [2]: linearity, symmetry, rigid-body null space, positive diagonal --
+    """BASELINE configs[1], [2] and the ~100 M-DoF box of configs[3] on one GPU: linearity, symmetry, rigid-body null space, positive diagonal --
     size-independent properties where the oracle is too slow to run."""
     import torch
     g = G.GpuProblem(problem, n, p)
