@@ -274,6 +274,12 @@ static int vec_release(CeedVector v, CeedMemType m) {
 }
 
 static int vec_sync(CeedVector v, CeedMemType m) {
+  if (v->length == 0) { /* empty vectors (a rank without elements) are always "valid" */
+    CeedChk(vec_alloc(v, m));
+    if (m == CEED_MEM_HOST) v->h_valid = 1;
+    else v->d_valid = 1;
+    return 0;
+  }
   if (m == CEED_MEM_HOST) {
     if (v->h_valid) return 0;
     if (!v->d_valid) return CeedError(v->ceed, 4, "CeedVector has no valid data (set it with CeedVectorSetArray/SetValue)");
