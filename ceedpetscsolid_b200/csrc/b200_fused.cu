@@ -66,7 +66,8 @@ template <int P, int Q, int PROB, int MODE>
 __global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? 5 : 2) : 1)
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
-              double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y) {
+              double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y,
+              const unsigned *__restrict__ scat_tab) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
   constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10;
@@ -85,6 +86,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   const int lane = t * ebn + eb;
   if (tid == 0) l2_prefetch_bulk(qslab, (unsigned)(ebt * Q * NC * sizeof(double)));
 
+  int *soff = reinterpret_cast<int *>(smem + EB * SE);
   // ---- phase 0: gather node z-lines, contract z with B
   if (act && a < P && b < P) {
     double r[3][P];
@@ -92,6 +94,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
 #pragma unroll
     for (int k = 0; k < P; k++) {
       const int o = __ldg(off + k * P * P);
+      soff[eb * P3 + (k * P + b) * P + a] = o;  // parked for the scatter at the end
 #pragma unroll
       for (int c = 0; c < 3; c++) r[c][k] = __ldg(x + o + c);
     }
@@ -309,18 +312,20 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
     }
   }
   __syncthreads();
-  // ---- scatter-add in L-vector order: consecutive lanes -> (node, component) pairs that are
-  // consecutive in memory for interlaced dofs, so one RED request touches few sectors
+  // ---- scatter-add in L-vector order: flat sweep f = (element, node, component), component fastest, so
+  // consecutive lanes hit consecutive L-vector entries (interlaced dofs) and one RED request touches few
+  // sectors.  The (lattice index, offset index, component) of each f is the same for every CTA: it comes
+  // from a small table (L1/L2 resident) instead of ~30 integer instructions of div/mod per entry.
   {
-    const int total = ebn * P3 * 3;
-    const int *offb = offsets + (size_t)blk * EB * P3;
-    for (int f = tid; f < total; f += Cfg<Q>::NT) {
-      const int el = f / (3 * P3), r = f - el * (3 * P3);
-      const int node = r / 3, c = r - node * 3;
-      const int i = node % P, j = (node / P) % P, k = node / (P * P);
-      const double v = smem[el * SE + IDX(c, i, j, k)];
-      atomicAdd(y + __ldg(offb + el * P3 + node) + c, v);
-    }
+    constexpr int NT = Cfg<Q>::NT, NIT = (EB * 3 * P3 + NT - 1) / NT;
+    const int total = ebn * 3 * P3;
+    unsigned u[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) u[it] = (tid + it * NT < total) ? __ldg(scat_tab + tid + it * NT) : 0u;
+#pragma unroll
+    for (int it = 0; it < NIT; it++)
+      if (tid + it * NT < total)
+        atomicAdd(y + soff[(u[it] >> 16) & 0xFFFu] + (u[it] >> 28), smem[u[it] & 0xFFFFu]);
   }
 }
 
@@ -628,14 +633,28 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
   for (int i = 0; i < Q * P; i++) m.B[i] = hB[i];
   if (collocated_grad(P, Q, hB, hD, m.Gc)) return set_error_msg("basis: no collocated gradient with Gc*B = D (rank-deficient interp1d)");
   auto kern = k_fused_apply<P, Q, PROB, MODE>;
+  constexpr int EB = Cfg<Q>::EB, P3 = P * P * P, SC = Cfg<Q>::SC, SZ = Cfg<Q>::SZ, SY = Cfg<Q>::SY;
+  const size_t smem_bytes = Cfg<Q>::SMEM + sizeof(int) * EB * P3;
   static bool configured = false;
+  static unsigned *d_tab = nullptr;  // per device in principle; one device per process here
   if (!configured) {
-    if (int rc = opt_in_smem(kern, Cfg<Q>::SMEM)) return rc;
+    if (int rc = opt_in_smem(kern, smem_bytes)) return rc;
+    // scatter table: f = (el, node, c) with c fastest -> lattice index | offset index << 16 | c << 28
+    static_assert(EB * Cfg<Q>::SE < 65536 && EB * P3 < 4096, "scatter table packing");
+    unsigned h[EB * P3 * 3];
+    for (int el = 0; el < EB; el++)
+      for (int node = 0; node < P3; node++)
+        for (int c = 0; c < 3; c++) {
+          const int i = node % P, j = (node / P) % P, k = node / (P * P);
+          h[(el * P3 + node) * 3 + c] = (unsigned)(el * Cfg<Q>::SE + IDX(c, i, j, k)) | ((unsigned)(el * P3 + node) << 16) | ((unsigned)c << 28);
+        }
+    B200_CHECK(cudaMalloc(&d_tab, sizeof h));
+    B200_CHECK(cudaMemcpy(d_tab, h, sizeof h, cudaMemcpyHostToDevice));
     configured = true;
   }
-  const int nblk = (nelem + Cfg<Q>::EB - 1) / Cfg<Q>::EB;
+  const int nblk = (nelem + EB - 1) / EB;
   if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<Q>::NT, Cfg<Q>::SMEM, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y);
+  kern<<<nblk, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y, d_tab);
   B200_LAUNCH_CHECK("k_fused_apply");
   return 0;
 }
