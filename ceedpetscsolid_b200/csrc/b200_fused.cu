@@ -63,7 +63,8 @@ enum { MODE_RESIDUAL = 0, MODE_JACOBIAN = 1 };
 template <int P, int Q, int PROB, int MODE>
 // min CTAs/SM: 5 x 128 threads caps the Jacobian kernels at 96 registers (no spills at P=Q=5) and
 // measured 3.5 % faster than 4 x 128 regs; the residual kernels keep all registers
-__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? 5 : 2) : 1)
+// (residual kernels: 4 CTAs/SM (128 registers, a few spilled words) measured 20 % faster than 1-2 CTAs at 228 registers)
+__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? 5 : 2) : (Cfg<Q>::NT <= 128 ? 4 : 1))
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y,
