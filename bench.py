@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--solve", action="store_true",
                     help="time the full Newton-Krylov-p-MG solve (BASELINE configs[4]) instead of the MatMult")
     ap.add_argument("--load-steps", type=int, default=10)
-    ap.add_argument("--coarse-rtol", type=float, default=1e-3)
+    ap.add_argument("--coarse-rtol", type=float, default=1e-2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

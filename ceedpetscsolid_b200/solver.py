@@ -388,7 +388,7 @@ class ColoredCoarseMatrix:
 class PMultigrid:
     """PCMG, multiplicative V-cycle, levels[0] = coarsest (p = 1) ... levels[-1] = finest."""
 
-    def __init__(self, V, levels, transfers, coarse_rtol=1e-3, coarse_maxit=500, smooth_its=3):
+    def __init__(self, V, levels, transfers, coarse_rtol=1e-2, coarse_maxit=500, smooth_its=3):
         """levels: list of objects with .n, .device, .jacobian(X, Y), .diagonal(D), .local_apply(xloc, yloc), .dm
         transfers[l] (l >= 1): object with .prolong(Xc, Yf), .restrict(Xf, Yc) between l-1 and l."""
         self.V, self.levels, self.transfers = V, levels, transfers
