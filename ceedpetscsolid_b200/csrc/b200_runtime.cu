@@ -66,6 +66,27 @@ __global__ void k_pcg_update(double *x, double *r, double *z, const double *p, c
     z[i] = dinv[i] * ri;
   }
 }
+// Chebyshev/Jacobi smoother, fused vector updates (one pass each instead of 3-4 BLAS-1 passes)
+//   init: d = dinv .* r * inv_theta;  x = zero_guess ? d : x + d
+//   step: r -= Ad;  d = c1 d + c2 dinv .* r;  x += d
+__global__ void k_cheb_init(double *x, const double *r, double *d, const double *dinv, double inv_theta, int zero_guess,
+                            size_t n) {
+  GRID_STRIDE(i, n) {
+    const double di = dinv[i] * r[i] * inv_theta;
+    d[i] = di;
+    x[i] = zero_guess ? di : x[i] + di;
+  }
+}
+__global__ void k_cheb_step(double *x, double *r, double *d, const double *Ad, const double *dinv, double c1, double c2,
+                            size_t n) {
+  GRID_STRIDE(i, n) {
+    const double ri = r[i] - Ad[i];
+    const double di = c1 * d[i] + c2 * (dinv[i] * ri);
+    r[i] = ri;
+    d[i] = di;
+    x[i] += di;
+  }
+}
 // 27-point vector stencil on a structured node lattice: vals[(o*3 + a)*n + row], o = (dx+1)+3(dy+1)+9(dz+1)
 __global__ void k_stencil27_spmv(int Nx, int Ny, int Nz, const double *__restrict__ vals, const double *__restrict__ x,
                                  double *__restrict__ y) {
@@ -260,6 +281,12 @@ int b200_vec_aypx_dev(double *y, const double *x, size_t n, const double *num, c
 int b200_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv, size_t n,
                     const double *rz, const double *pAp) {
   VEC_KERNEL((k_pcg_update<<<grid_for(n, 256), 256, 0, g_stream>>>(x, r, z, p, Ap, dinv, n, rz, pAp)), n);
+}
+int b200_cheb_init(double *x, const double *r, double *d, const double *dinv, double inv_theta, int zero_guess, size_t n) {
+  VEC_KERNEL((k_cheb_init<<<grid_for(n, 256), 256, 0, g_stream>>>(x, r, d, dinv, inv_theta, zero_guess, n)), n);
+}
+int b200_cheb_step(double *x, double *r, double *d, const double *Ad, const double *dinv, double c1, double c2, size_t n) {
+  VEC_KERNEL((k_cheb_step<<<grid_for(n, 256), 256, 0, g_stream>>>(x, r, d, Ad, dinv, c1, c2, n)), n);
 }
 int b200_stencil27_spmv(int Nx, int Ny, int Nz, const double *vals, const double *x, double *y) {
   const size_t n = (size_t)3 * Nx * Ny * Nz;

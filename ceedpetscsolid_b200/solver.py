@@ -281,22 +281,33 @@ class ChebyshevJacobi:
         rho = 1.0 / sigma
         r, z, d, Ad = self.r, self.z, self.d, self.Ad
         if zero_guess:
-            V.zero(x)
             V.copy(r, b)
         else:
             A(x, Ad)
             V.axpby(r, 1.0, b, -1.0, Ad)
-        V.pmult(z, self.dinv, r)
-        V.axpby(d, 1.0 / theta, z, 0.0, z)
-        for k in range(self.its):
-            V.axpy(x, 1.0, d)
-            if k + 1 == self.its:
-                break
+        # x_{k+1} = x_k + d_k;  r_{k+1} = r_k - A d_k;  d_{k+1} = rho' rho d_k + (2 rho'/delta) D^-1 r_{k+1}
+        if x.is_cuda:
+            b2(lib.b200_cheb_init(x.data_ptr(), r.data_ptr(), d.data_ptr(), self.dinv.data_ptr(), 1.0 / theta,
+                                  1 if zero_guess else 0, x.numel()))
+        else:
+            torch.mul(self.dinv, r, out=d)
+            d.mul_(1.0 / theta)
+            if zero_guess:
+                x.copy_(d)
+            else:
+                x.add_(d)
+        for _ in range(self.its - 1):
             A(d, Ad)
-            V.axpy(r, -1.0, Ad)
-            V.pmult(z, self.dinv, r)
             rho_new = 1.0 / (2.0 * sigma - rho)
-            V.axpby(d, rho_new * rho, d, 2.0 * rho_new / delta, z)
+            c1, c2 = rho_new * rho, 2.0 * rho_new / delta
+            if x.is_cuda:
+                b2(lib.b200_cheb_step(x.data_ptr(), r.data_ptr(), d.data_ptr(), Ad.data_ptr(), self.dinv.data_ptr(), c1, c2,
+                                      x.numel()))
+            else:
+                r.sub_(Ad)
+                torch.mul(self.dinv, r, out=z)
+                d.mul_(c1).add_(z, alpha=c2)
+                x.add_(d)
             rho = rho_new
 
 

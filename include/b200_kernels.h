@@ -98,6 +98,11 @@ int b200_vec_axpy_dev(double *y, const double *x, size_t n, const double *num, c
 int b200_vec_aypx_dev(double *y, const double *x, size_t n, const double *num, const double *den);
 int b200_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv, size_t n,
                     const double *rz, const double *pAp);
+/* Chebyshev + point-Jacobi smoother (elasticity.c:539-552), fused vector updates:
+ *   init: d = dinv .* r * inv_theta;  x = zero_guess ? d : x + d
+ *   step: r -= Ad;  d = c1 d + c2 dinv .* r;  x += d */
+int b200_cheb_init(double *x, const double *r, double *d, const double *dinv, double inv_theta, int zero_guess, size_t n);
+int b200_cheb_step(double *x, double *r, double *d, const double *Ad, const double *dinv, double c1, double c2, size_t n);
 /* assembled coarse operator on a structured (Nx,Ny,Nz) node lattice, 3 dofs per node, as a 27-point block
  * stencil: vals[((dx+1)+3(dy+1)+9(dz+1))*3 + a][row]; y = A x */
 int b200_stencil27_spmv(int Nx, int Ny, int Nz, const double *vals, const double *x, double *y);
