@@ -130,6 +130,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
     gmesh = BoxMesh(n=n, perturb=app.perturb, seed=0, lengths=lengths)
     el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank, gmesh=gmesh,
                     coarse_rtol=args.coarse_rtol)
+    el.pc.coarse_maxit = args.coarse_maxit
     libceed.launch_count_reset()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -173,6 +174,7 @@ def main():
                     help="time the full Newton-Krylov-p-MG solve (BASELINE configs[4]) instead of the MatMult")
     ap.add_argument("--load-steps", type=int, default=10)
     ap.add_argument("--coarse-rtol", type=float, default=1e-2)
+    ap.add_argument("--coarse-maxit", type=int, default=500)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
