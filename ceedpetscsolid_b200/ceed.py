@@ -135,6 +135,8 @@ _proto("b200_vec_axpy_dev", _vp, _vp, _sz, _vp, _vp, _d)
 _proto("b200_vec_aypx_dev", _vp, _vp, _sz, _vp, _vp)
 _proto("b200_pcg_update", _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp)
 _proto("b200_stencil27_spmv", _i, _i, _i, _vp, _vp, _vp)
+_proto("b200_lattice_prolong", _i, _i, _i, _vp, _vp)
+_proto("b200_lattice_restrict", _i, _i, _i, _vp, _vp)
 _proto("b200_cheb_init", _vp, _vp, _vp, _vp, _d, _i, _sz)
 _proto("b200_cheb_step", _vp, _vp, _vp, _vp, _vp, _d, _d, _sz)
 _proto("b200_vec_reciprocal", _vp, _sz)

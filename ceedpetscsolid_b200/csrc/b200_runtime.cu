@@ -87,6 +87,46 @@ __global__ void k_cheb_step(double *x, double *r, double *d, const double *Ad, c
     x[i] += di;
   }
 }
+// Trilinear transfer between nested structured node lattices (coarse Nc -> fine 2Nc-1 per axis), 3 dofs per node.
+// prolong: xf = P xc;   restrict: xc = P^T xf   (gather form: each output entry is written by one thread)
+__global__ void k_lattice_prolong(int Ncx, int Ncy, int Ncz, const double *__restrict__ xc, double *__restrict__ xf) {
+  const int Nfx = 2 * Ncx - 1, Nfy = 2 * Ncy - 1, Nfz = 2 * Ncz - 1;
+  const size_t n = (size_t)3 * Nfx * Nfy * Nfz;
+  GRID_STRIDE(row, n) {
+    const int a = (int)(row % 3), node = (int)(row / 3);
+    const int i = node % Nfx, j = (node / Nfx) % Nfy, k = node / (Nfx * Nfy);
+    const int i0 = i >> 1, j0 = j >> 1, k0 = k >> 1, di = i & 1, dj = j & 1, dk = k & 1;
+    double s = 0;
+    for (int c = 0; c <= dk; c++)
+      for (int b = 0; b <= dj; b++)
+        for (int e = 0; e <= di; e++) s += xc[(size_t)3 * ((i0 + e) + Ncx * ((j0 + b) + (size_t)Ncy * (k0 + c))) + a];
+    xf[row] = s * (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+  }
+}
+__global__ void k_lattice_restrict(int Ncx, int Ncy, int Ncz, const double *__restrict__ xf, double *__restrict__ xc) {
+  const int Nfx = 2 * Ncx - 1, Nfy = 2 * Ncy - 1, Nfz = 2 * Ncz - 1;
+  const size_t n = (size_t)3 * Ncx * Ncy * Ncz;
+  GRID_STRIDE(row, n) {
+    const int a = (int)(row % 3), node = (int)(row / 3);
+    const int I = node % Ncx, J = (node / Ncx) % Ncy, K = node / (Ncx * Ncy);
+    double s = 0;
+    for (int dk = -1; dk <= 1; dk++) {
+      const int k = 2 * K + dk;
+      if (k < 0 || k >= Nfz) continue;
+      for (int dj = -1; dj <= 1; dj++) {
+        const int j = 2 * J + dj;
+        if (j < 0 || j >= Nfy) continue;
+        for (int di = -1; di <= 1; di++) {
+          const int i = 2 * I + di;
+          if (i < 0 || i >= Nfx) continue;
+          const double w = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+          s += w * xf[(size_t)3 * (i + Nfx * (j + (size_t)Nfy * k)) + a];
+        }
+      }
+    }
+    xc[row] = s;
+  }
+}
 // 27-point vector stencil on a structured node lattice: vals[(o*3 + a)*n + row], o = (dx+1)+3(dy+1)+9(dz+1)
 __global__ void k_stencil27_spmv(int Nx, int Ny, int Nz, const double *__restrict__ vals, const double *__restrict__ x,
                                  double *__restrict__ y) {
@@ -287,6 +327,14 @@ int b200_cheb_init(double *x, const double *r, double *d, const double *dinv, do
 }
 int b200_cheb_step(double *x, double *r, double *d, const double *Ad, const double *dinv, double c1, double c2, size_t n) {
   VEC_KERNEL((k_cheb_step<<<grid_for(n, 256), 256, 0, g_stream>>>(x, r, d, Ad, dinv, c1, c2, n)), n);
+}
+int b200_lattice_prolong(int Ncx, int Ncy, int Ncz, const double *xc, double *xf) {
+  const size_t n = (size_t)3 * (2 * Ncx - 1) * (2 * Ncy - 1) * (2 * Ncz - 1);
+  VEC_KERNEL((k_lattice_prolong<<<grid_for(n, 256), 256, 0, g_stream>>>(Ncx, Ncy, Ncz, xc, xf)), n);
+}
+int b200_lattice_restrict(int Ncx, int Ncy, int Ncz, const double *xf, double *xc) {
+  const size_t n = (size_t)3 * Ncx * Ncy * Ncz;
+  VEC_KERNEL((k_lattice_restrict<<<grid_for(n, 256), 256, 0, g_stream>>>(Ncx, Ncy, Ncz, xf, xc)), n);
 }
 int b200_stencil27_spmv(int Nx, int Ny, int Nz, const double *vals, const double *x, double *y) {
   const size_t n = (size_t)3 * Nx * Ny * Nz;

@@ -61,6 +61,23 @@ class AppCtx:
     clamp: dict = field(default_factory=lambda: {(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
 
 
+def build_h_dms(gmesh, grid, rank, world, faces, device, dist=None, min_elems=2):
+    """LevelDMs (degree 1) of successively halved box meshes below the p = 1 level, for the h-multigrid coarse
+    solve.  Halving stops when a brick would have an odd element count or fewer than `min_elems` per axis."""
+    dms = []
+    n = gmesh.n
+    while all(v % (2 * grid[d]) == 0 and v // (2 * grid[d]) >= min_elems for d, v in enumerate(n)):
+        n = tuple(v // 2 for v in n)
+        gm = BoxMesh(n=n, lengths=gmesh.lengths)
+        mesh = gm.brick(grid, rank) if world > 1 else gm
+        halo = None
+        if world > 1:
+            from .halo import Halo
+            halo = Halo(gm, grid, rank, 1, dist, device=device if isinstance(device, str) and device == "cpu" else None)
+        dms.append(matops.LevelDM(mesh, 1, bc_faces=faces, halo=halo, device=device, shared=True))
+    return dms
+
+
 class GpuLevel:
     """One p-multigrid level on the /gpu/b200 backend (the MatShell of elasticity.c:392-411)."""
 
@@ -116,7 +133,7 @@ class GpuTransfer:
 class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
-    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2):
+    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg"):
         self.app, self.dist = app, dist
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
@@ -166,7 +183,12 @@ class Elasticity:
             if dm.dot_weight is not None:
                 self.V.weights[dm.nglobal] = dm.dot_weight
                 self.V.consistent[dm.nglobal] = dm.make_consistent
-        self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol)
+        h_dms = build_h_dms(self.gmesh, grid, rank, world, faces, f"cuda:{device_id}", dist) if coarse == "hmg" else None
+        for dm in (h_dms or []):
+            if dm.dot_weight is not None:
+                self.V.weights[dm.nglobal] = dm.dot_weight
+                self.V.consistent[dm.nglobal] = dm.make_consistent
+        self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol, h_dms=h_dms)
         self.U = self.dms[fine].create_global_vector()
 
     @staticmethod

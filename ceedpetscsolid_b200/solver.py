@@ -381,16 +381,165 @@ class ColoredCoarseMatrix:
         self.stencil_src = torch.from_numpy(src).to(self.dm.device)
         self.svals = torch.zeros((81, n), dtype=torch.float64, device=self.dm.device)
 
+    def local_mult(self, xloc, yloc):
+        """y_loc = A_loc x_loc (the rank-local, un-assembled matrix)"""
+        if xloc.is_cuda:
+            b2(lib.b200_stencil27_spmv(self.N[0], self.N[1], self.N[2], self.svals.data_ptr(), xloc.data_ptr(),
+                                       yloc.data_ptr()))
+        else:
+            c = self.cols.long().clamp_min(0)
+            yloc.copy_((self.vals * xloc[c] * (self.cols >= 0)).sum(0))
+
     def mult(self, X, Y):
         dm = self.dm
         dm.zero_and_global_to_local(X, self.Xloc)
-        if self.Xloc.is_cuda:
-            b2(lib.b200_stencil27_spmv(self.N[0], self.N[1], self.N[2], self.svals.data_ptr(), self.Xloc.data_ptr(),
-                                       self.Yloc.data_ptr()))
-        else:
-            c = self.cols.long().clamp_min(0)
-            self.Yloc.copy_((self.vals * self.Xloc[c] * (self.cols >= 0)).sum(0))
+        self.local_mult(self.Xloc, self.Yloc)
         dm.local_to_global(self.Yloc, Y)
+
+    def diagonal(self, D):
+        """global diagonal: centre-block diagonal of the local stencil, summed over ranks"""
+        n = self.dm.lsize
+        rows = torch.arange(n, device=self.dm.device)
+        slot = 13 * 3 + (rows % 3)                       # centre neighbour (dx=dy=dz=0), same component
+        self.Yloc.copy_(self.svals[slot, rows])
+        self.dm.local_to_global(self.Yloc, D)
+
+
+class HMultigrid:
+    """Geometric h-multigrid on the assembled p = 1 level: the stand-in for GAMG (elasticity.c:569-585).
+
+    Level 0 is the colouring-assembled p = 1 matrix; every further level halves the element count per
+    axis.  Coarse matrices are Galerkin products A_H = P^T A_h P with trilinear P in index space, assembled
+    by the SAME colouring procedure (81 applications of the rank-local P^T A_h P); one V(2,2) cycle with
+    Chebyshev/Jacobi smoothing is a fixed linear operator, so the outer CG theory holds, and its cost does
+    not grow with the mesh the way Jacobi-PCG iterations do.  Brick partitions stay aligned because every
+    brick is coarsened in place; the coarsest level is solved by Jacobi-PCG."""
+
+    def __init__(self, V, fine_matrix, dms, smooth_its=2, coarsest_rtol=1e-2):
+        """fine_matrix: ColoredCoarseMatrix of the p = 1 level; dms: LevelDMs of the h-levels, dms[0] = its dm."""
+        self.V, self.dms, self.smooth_its, self.coarsest_rtol = V, dms, smooth_its, coarsest_rtol
+        self.mats = [fine_matrix]
+        for l in range(1, len(dms)):
+            self.mats.append(ColoredCoarseMatrix(dms[l], self._galerkin_apply(l)))
+        mk = lambda l: torch.zeros(dms[l].nglobal, dtype=torch.float64, device=dms[l].device)
+        mkl = lambda l: torch.zeros(dms[l].lsize, dtype=torch.float64, device=dms[l].device)
+        L = len(dms)
+        self.b, self.x, self.r, self.t, self.diag = ([mk(l) for l in range(L)] for _ in range(5))
+        self.lf, self.lf2, self.lc = [mkl(l) for l in range(L)], [mkl(l) for l in range(L)], [mkl(l) for l in range(L)]
+        self.smoothers = [ChebyshevJacobi(V, self.mats[l].mult, dms[l].nglobal, dms[l].device, smooth_its, seed=100 + l)
+                          for l in range(L - 1)]
+        self.cwork = [mk(L - 1) for _ in range(4)]
+        self.cdinv = mk(L - 1)
+        self.coarsest_its = 0
+
+    # ---- rank-local trilinear transfer between lattice l-1 (fine) and l (coarse)
+    def _P(self, l, xc_loc, xf_loc):
+        N = self.dms[l].mesh.nodes_per_dim(1)
+        if xc_loc.is_cuda:
+            b2(lib.b200_lattice_prolong(N[0], N[1], N[2], xc_loc.data_ptr(), xf_loc.data_ptr()))
+        else:
+            xf_loc.copy_(_lattice_prolong_cpu(N, xc_loc))
+
+    def _PT(self, l, xf_loc, xc_loc):
+        N = self.dms[l].mesh.nodes_per_dim(1)
+        if xf_loc.is_cuda:
+            b2(lib.b200_lattice_restrict(N[0], N[1], N[2], xf_loc.data_ptr(), xc_loc.data_ptr()))
+        else:
+            xc_loc.copy_(_lattice_restrict_cpu(N, xf_loc))
+
+    def _galerkin_apply(self, l):
+        def apply(xc_loc, yc_loc):  # y = P^T A_{l-1,loc} P x on local lattices, no communication
+            self._P(l, xc_loc, self.lf[l - 1])
+            self.mats[l - 1].local_mult(self.lf[l - 1], self.lf2[l - 1])
+            self._PT(l, self.lf2[l - 1], yc_loc)
+        return apply
+
+    def setup(self):
+        """after the p = 1 matrix has been assembled: Galerkin levels, diagonals, eigen-estimates"""
+        for l in range(1, len(self.dms)):
+            self.mats[l].assemble()
+        for l, m in enumerate(self.mats):
+            m.diagonal(self.diag[l])
+            if l < len(self.mats) - 1:
+                self.smoothers[l].setup(self.diag[l])
+        self.cdinv.copy_(1.0 / self.diag[-1])
+
+    def _restrict(self, l, Xf, Xc):  # level l-1 -> l
+        dmf, dmc = self.dms[l - 1], self.dms[l]
+        src = Xf
+        if dmf.dot_weight is not None:  # shared-dof vectors: count every fine dof once across ranks
+            src = self.t[l - 1]
+            self.V.pmult(src, Xf, dmf.dot_weight)
+        dmf.zero_and_global_to_local(src, self.lf[l - 1])
+        self._PT(l, self.lf[l - 1], self.lc[l])
+        dmc.local_to_global(self.lc[l], Xc)
+
+    def _prolong(self, l, Xc, Xf):  # level l -> l-1 (every copy of a shared dof gets the same value: no exchange)
+        dmf, dmc = self.dms[l - 1], self.dms[l]
+        dmc.zero_and_global_to_local(Xc, self.lc[l])
+        self._P(l, self.lc[l], self.lf[l - 1])
+        if Xf.is_cuda:
+            b2(lib.b200_gather(Xf.data_ptr(), self.lf[l - 1].data_ptr(), dmf.free_owned_idx.data_ptr(), dmf.nglobal))
+        else:
+            Xf.copy_(self.lf[l - 1][dmf.free_owned_idx.long()])
+
+    def _cycle(self, l):
+        V = self.V
+        if l == len(self.dms) - 1:
+            self.coarsest_its += jacobi_pcg_nosync(V, self.mats[l].mult, self.cdinv, self.b[l], self.x[l], self.cwork,
+                                                   self.coarsest_rtol, 200)
+            return
+        sm = self.smoothers[l]
+        sm.apply(self.b[l], self.x[l], zero_guess=True)
+        self.mats[l].mult(self.x[l], self.t[l])
+        V.axpby(self.r[l], 1.0, self.b[l], -1.0, self.t[l])
+        self._restrict(l + 1, self.r[l], self.b[l + 1])
+        self._cycle(l + 1)
+        self._prolong(l + 1, self.x[l + 1], self.t[l])
+        V.axpy(self.x[l], 1.0, self.t[l])
+        sm.apply(self.b[l], self.x[l], zero_guess=False)
+
+    def solve(self, b, x):
+        self.b[0].copy_(b)
+        self._cycle(0)
+        x.copy_(self.x[0])
+
+
+def _lattice_prolong_cpu(Nc, xc):
+    """xf = P xc on CPU tensors (oracle runs): trilinear, fine lattice 2Nc-1 per axis, 3 dofs per node"""
+    c = xc.reshape(Nc[2], Nc[1], Nc[0], 3)
+    for ax in range(3):
+        n = c.shape[ax]
+        shp = list(c.shape)
+        shp[ax] = 2 * n - 1
+        f = torch.zeros(shp, dtype=c.dtype)
+        idx_e = [slice(None)] * 4
+        idx_o = [slice(None)] * 4
+        lo, hi = [slice(None)] * 4, [slice(None)] * 4
+        idx_e[ax] = slice(0, None, 2)
+        idx_o[ax] = slice(1, None, 2)
+        lo[ax], hi[ax] = slice(0, n - 1), slice(1, n)
+        f[tuple(idx_e)] = c
+        f[tuple(idx_o)] = 0.5 * (c[tuple(lo)] + c[tuple(hi)])
+        c = f
+    return c.reshape(-1)
+
+
+def _lattice_restrict_cpu(Nc, xf):
+    """xc = P^T xf on CPU tensors"""
+    f = xf.reshape(2 * Nc[2] - 1, 2 * Nc[1] - 1, 2 * Nc[0] - 1, 3)
+    for ax in range(3):
+        n = (f.shape[ax] + 1) // 2
+        idx_e, idx_o = [slice(None)] * 4, [slice(None)] * 4
+        idx_e[ax], idx_o[ax] = slice(0, None, 2), slice(1, None, 2)
+        c = f[tuple(idx_e)].clone()
+        odd = f[tuple(idx_o)]
+        lo, hi = [slice(None)] * 4, [slice(None)] * 4
+        lo[ax], hi[ax] = slice(0, n - 1), slice(1, n)
+        c[tuple(lo)] += 0.5 * odd
+        c[tuple(hi)] += 0.5 * odd
+        f = c
+    return f.reshape(-1)
 
 
 # --------------------------------------------------------------------------- PCMG + Newton
@@ -399,7 +548,7 @@ class ColoredCoarseMatrix:
 class PMultigrid:
     """PCMG, multiplicative V-cycle, levels[0] = coarsest (p = 1) ... levels[-1] = finest."""
 
-    def __init__(self, V, levels, transfers, coarse_rtol=1e-2, coarse_maxit=500, smooth_its=3):
+    def __init__(self, V, levels, transfers, coarse_rtol=1e-2, coarse_maxit=500, smooth_its=3, h_dms=None):
         """levels: list of objects with .n, .device, .jacobian(X, Y), .diagonal(D), .local_apply(xloc, yloc), .dm
         transfers[l] (l >= 1): object with .prolong(Xc, Yf), .restrict(Xf, Yc) between l-1 and l."""
         self.V, self.levels, self.transfers = V, levels, transfers
@@ -414,6 +563,9 @@ class PMultigrid:
         self.t = [mk(l) for l in range(L)]
         self.diag = [mk(l) for l in range(L)]
         self.coarse = ColoredCoarseMatrix(levels[0].dm, levels[0].local_apply)
+        # h_dms: LevelDMs of successively halved meshes below the p = 1 level -> geometric multigrid coarse
+        # solve (GAMG stand-in); None -> Jacobi-PCG on the assembled p = 1 matrix
+        self.hmg = HMultigrid(V, self.coarse, [levels[0].dm] + list(h_dms)) if h_dms else None
         self.cwork = [mk(0) for _ in range(4)]
         self.cdinv = mk(0)
         self.coarse_its = 0
@@ -428,8 +580,15 @@ class PMultigrid:
                 self.smoothers[l].setup(self.diag[l])
         self.coarse.assemble()
         self.cdinv.copy_(1.0 / self.diag[0])
+        if self.hmg is not None:
+            self.hmg.setup()
 
     def _coarse_solve(self, b, x):
+        if self.hmg is not None:
+            self.hmg.solve(b, x)
+            self.coarse_solves += 1
+            self.coarse_its = self.hmg.coarsest_its
+            return
         its = jacobi_pcg_nosync(self.V, self.coarse.mult, self.cdinv, b, x, self.cwork, self.coarse_rtol,
                                 self.coarse_maxit)
         self.coarse_its += its

@@ -98,6 +98,10 @@ int b200_vec_axpy_dev(double *y, const double *x, size_t n, const double *num, c
 int b200_vec_aypx_dev(double *y, const double *x, size_t n, const double *num, const double *den);
 int b200_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv, size_t n,
                     const double *rz, const double *pAp);
+/* trilinear transfer between nested structured node lattices (coarse Nc, fine 2Nc-1 per axis), 3 dofs per node:
+ * the h-multigrid that stands in for GAMG on the assembled p = 1 level (elasticity.c:569-585) */
+int b200_lattice_prolong(int Ncx, int Ncy, int Ncz, const double *xc, double *xf);   /* xf = P xc   */
+int b200_lattice_restrict(int Ncx, int Ncy, int Ncz, const double *xf, double *xc);  /* xc = P^T xf */
 /* Chebyshev + point-Jacobi smoother (elasticity.c:539-552), fused vector updates:
  *   init: d = dinv .* r * inv_theta;  x = zero_guess ? d : x + d
  *   step: r -= Ad;  d = c1 d + c2 dinv .* r;  x += d */

@@ -91,13 +91,16 @@ class OracleTransfer:
         self.c.dm.local_to_global(torch.from_numpy(y), Yc)
 
 
-def oracle_solve(app, log=None, **kw):
+def oracle_solve(app, log=None, coarse="hmg", **kw):
+    from ceedpetscsolid_b200.elasticity import build_h_dms
     sh = OracleShared(app)
     L = len(sh.degrees)
     levels = [OracleLevel(sh, l, l == L - 1) for l in range(L)]
     transfers = [None] + [OracleTransfer(sh, levels[l - 1], levels[l]) for l in range(1, L)]
     V = solver.Vec(None)
-    pc = solver.PMultigrid(V, levels, transfers)
+    faces = "all" if app.test_mode else list(app.clamp.keys())
+    h_dms = build_h_dms(sh.mesh, (1, 1, 1), 0, 1, faces, "cpu") if coarse == "hmg" else None
+    pc = solver.PMultigrid(V, levels, transfers, h_dms=h_dms)
     U = levels[-1].dm.create_global_vector(matops.MEM_HOST)
     out = solver.newton_solve(V, levels[-1], pc, U, num_increments=app.num_steps, log=log, **kw)
     return out, U
