@@ -129,7 +129,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                  clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1 * lengths[2], 0, 0, 1, 0]})
     gmesh = BoxMesh(n=n, perturb=app.perturb, seed=0, lengths=lengths)
     el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank, gmesh=gmesh,
-                    coarse_rtol=args.coarse_rtol, coarse=args.coarse)
+                    coarse_rtol=args.coarse_rtol, coarse=args.coarse, assemble=args.assemble)
     el.pc.coarse_maxit = args.coarse_maxit
     libceed.launch_count_reset()
     sampler = ClockSampler(local_rank)
@@ -150,7 +150,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                           "warmup": 0, "ms_per_step": float(t.item()) * 1e3, "higher_is_better": False,
                           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "snes_its": out["snes_its"], "ksp_its": out["ksp_its"], "converged": out["converged"],
-                          "coarse_pcg_its": out["coarse_its"], "coarse_rtol": args.coarse_rtol, "coarse": args.coarse, "dofs_unconstrained": out["dofs_global_unconstrained"],
+                          "coarse_pcg_its": out["coarse_its"], "coarse_rtol": args.coarse_rtol, "coarse": args.coarse, "assemble": args.assemble, "dofs_unconstrained": out["dofs_global_unconstrained"],
                           "mdofs_per_sec_in_snes": out["mdofs_per_sec_in_snes"], "gpu_launches": int(libceed.launch_count()),
                           "clocks": clocks}))
     if world > 1:
@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--load-steps", type=int, default=10)
     ap.add_argument("--coarse-rtol", type=float, default=1e-2)
     ap.add_argument("--coarse-maxit", type=int, default=500)
+    ap.add_argument("--assemble", default="coo", choices=["coo", "color"], help="p=1 matrix: CeedOperatorLinearAssemble element matrices, or 81 coloured applies (misc.c:151-183)")
     ap.add_argument("--coarse", default="hmg", choices=["hmg", "pcg"], help="coarse solve on the assembled p=1 level: h-multigrid (GAMG stand-in) or Jacobi-PCG")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -101,6 +101,8 @@ _proto("CeedOperatorApply", _vp, _vp, _vp, _vp)
 _proto("CeedOperatorApplyAdd", _vp, _vp, _vp, _vp)
 _proto("CeedOperatorLinearAssembleDiagonal", _vp, _vp, _vp)
 _proto("CeedOperatorLinearAssembleAddDiagonal", _vp, _vp, _vp)
+_proto("CeedOperatorLinearAssembleSymbolic", _vp, C.POINTER(_i), C.POINTER(C.POINTER(_i)), C.POINTER(C.POINTER(_i)))
+_proto("CeedOperatorLinearAssemble", _vp, _vp)
 _proto("CeedOperatorDestroy", _pvp)
 _proto("CeedOperatorIsFusedB200", _vp, C.POINTER(_i))
 _proto("CeedB200LaunchCount", restype=C.c_ulonglong)
@@ -135,6 +137,7 @@ _proto("b200_vec_axpy_dev", _vp, _vp, _sz, _vp, _vp, _d)
 _proto("b200_vec_aypx_dev", _vp, _vp, _sz, _vp, _vp)
 _proto("b200_pcg_update", _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp)
 _proto("b200_stencil27_spmv", _i, _i, _i, _vp, _vp, _vp)
+_proto("b200_stencil27_galerkin", _i, _i, _i, _vp, _vp)
 _proto("b200_lattice_prolong", _i, _i, _i, _vp, _vp)
 _proto("b200_lattice_restrict", _i, _i, _i, _vp, _vp)
 _proto("b200_cheb_init", _vp, _vp, _vp, _vp, _d, _i, _sz)
@@ -428,6 +431,23 @@ class Operator(_Obj):
 
     def linear_assemble_diagonal(self, assembled):
         self._chk(lib.CeedOperatorLinearAssembleDiagonal(self.h, assembled.h, REQUEST_IMMEDIATE))
+
+    def linear_assemble_symbolic(self):
+        """(rows, cols) int32 numpy arrays of the COO pattern (CeedOperatorLinearAssembleSymbolic)."""
+        import numpy as np
+        n = C.c_int()
+        rows, cols = C.POINTER(_i)(), C.POINTER(_i)()
+        self._chk(lib.CeedOperatorLinearAssembleSymbolic(self.h, C.byref(n), C.byref(rows), C.byref(cols)))
+        r = np.ctypeslib.as_array(rows, shape=(max(n.value, 1),))[:n.value].copy()
+        c = np.ctypeslib.as_array(cols, shape=(max(n.value, 1),))[:n.value].copy()
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(rows)
+        libc.free(cols)
+        return r, c
+
+    def linear_assemble(self, values):
+        self._chk(lib.CeedOperatorLinearAssemble(self.h, values.h))
 
     @property
     def is_fused(self):

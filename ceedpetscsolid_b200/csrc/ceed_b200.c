@@ -1162,6 +1162,58 @@ int CeedOperatorLinearAssembleDiagonal(CeedOperator op, CeedVector assembled, Ce
   return CeedOperatorLinearAssembleAddDiagonal(op, assembled, request);
 }
 
+/* COO assembly: entry (e, col, row) of element e sits at (e*24 + col)*24 + row, element dof = node*3 + comp */
+static int op_assemblable(CeedOperator op) {
+  Ceed ceed = op->ceed;
+  if (op->composite) return CeedError(ceed, 1, "CeedOperatorLinearAssemble: composite operators are not supported by /gpu/b200");
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  if (!(op->kind == OP_FUSED_JACOBIAN || (op->kind == OP_FUSED_RESIDUAL && op->problem == B200_PROB_LINELAS)) ||
+      op->in[0].b->P != 2)
+    return CeedError(ceed, 1, "CeedOperatorLinearAssemble: /gpu/b200 assembles fused Jacobian operators on a trilinear "
+                              "(P = 2) level only (operator %s, P = %d); there is no CPU fallback",
+                     op->qf->name, op->in[0].b ? op->in[0].b->P : 0);
+  return 0;
+}
+
+int CeedOperatorLinearAssembleSymbolic(CeedOperator op, CeedInt *num_entries, CeedInt **rows, CeedInt **cols) {
+  Ceed ceed = op->ceed;
+  CeedChk(op_assemblable(op));
+  CeedElemRestriction r = op->in[0].r;
+  const size_t nelem = (size_t)r->nelem, ne = nelem * 576;
+  if (ne > 2147483647u) return CeedError(ceed, 1, "CeedOperatorLinearAssembleSymbolic: %zu entries overflow CeedInt", ne);
+  int *off = (int *)malloc(sizeof(int) * (nelem * 8 + 1));
+  *rows = (CeedInt *)malloc(sizeof(CeedInt) * (ne + 1));
+  *cols = (CeedInt *)malloc(sizeof(CeedInt) * (ne + 1));
+  if (!off || !*rows || !*cols) { free(off); free(*rows); free(*cols); return CeedError(ceed, 3, "out of memory"); }
+  if (nelem) B2(ceed, b200_memcpy_d2h(off, r->d_offsets, sizeof(int) * nelem * 8));
+  for (size_t e = 0; e < nelem; e++)
+    for (int c = 0; c < 24; c++)
+      for (int w = 0; w < 24; w++) {
+        (*rows)[(e * 24 + c) * 24 + w] = off[e * 8 + w / 3] + (w % 3) * r->compstride;
+        (*cols)[(e * 24 + c) * 24 + w] = off[e * 8 + c / 3] + (c % 3) * r->compstride;
+      }
+  free(off);
+  *num_entries = (CeedInt)ne;
+  return 0;
+}
+
+int CeedOperatorLinearAssemble(CeedOperator op, CeedVector values) {
+  Ceed ceed = op->ceed;
+  CeedChk(op_assemblable(op));
+  OpField *u = &op->in[0];
+  if ((size_t)values->length < (size_t)u->r->nelem * 576)
+    return CeedError(ceed, 1, "CeedOperatorLinearAssemble: values vector holds %d entries, %zu needed", values->length,
+                     (size_t)u->r->nelem * 576);
+  b200_physics phys;
+  CeedChk(qf_physics(op->qf, &phys));
+  const double *jc;
+  double *v;
+  CeedChk(jcache_get(op, &jc));
+  CeedChk(vec_dev_write(values, &v));
+  B2(ceed, b200_assemble_p1(op->problem, &phys, u->r->nelem, u->b->Q, u->b->interp1d, u->b->grad1d, jc, v));
+  return 0;
+}
+
 int CeedOperatorDestroy(CeedOperator *op) {
   if (!op || !*op) return 0;
   CeedOperator o = *op;

@@ -91,6 +91,25 @@ class GpuLevel:
     def diagonal(self, D):
         matops.GetDiag_Ceed(self.user, D)
 
+    coo = None
+
+    def enable_coo(self, ceed, mesh):
+        """Coarse (trilinear) level: assemble element matrices with CeedOperatorLinearAssemble (one pass over the
+        Jacobian cache) instead of colouring the operator (misc.c:151-183)."""
+        level = self
+
+        class _Coo:
+            elem_nodes = torch.from_numpy(mesh.offsets(1).reshape(-1, 8) // 3).to(self.device)
+            vals = torch.zeros(elem_nodes.shape[0] * 576, dtype=torch.float64, device=self.device)
+            vec = ceed.Vector(vals.numel())
+
+            def values(self):
+                self.vec.set_array(self.vals, level.user.memType)
+                level.user.op.linear_assemble(self.vec)
+                self.vec.take_array(level.user.memType)
+                return self.vals
+        self.coo = _Coo()
+
     def local_apply(self, xloc, yloc):
         u = self.user
         u.Xceed.set_array(xloc, u.memType)
@@ -133,7 +152,8 @@ class GpuTransfer:
 class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
-    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg"):
+    def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg",
+                 assemble="coo"):
         self.app, self.dist = app, dist
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
@@ -161,6 +181,8 @@ class Elasticity:
                                         phys=self.phys, memType=fu.memType, bc_values=self._bc_values_fn(self.dms[fine], app))
         self.levels = [GpuLevel(self.dms[l], self.users[l], self.res_user if l == fine else None)
                        for l in range(len(self.degrees))]
+        if assemble == "coo" and self.degrees[0] == 1 and self.users[0].op.is_fused:
+            self.levels[0].enable_coo(self.ceed, self.mesh)
         self.transfers = [None]
         for l in range(1, len(self.degrees)):
             pr = matops.setup_prolong_restrict_ctx(self.dms[l - 1], self.dms[l], self.ceed, self.data[l - 1], self.data[l],

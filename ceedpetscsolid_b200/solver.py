@@ -320,8 +320,13 @@ class ColoredCoarseMatrix:
     space of the rank (27 node colours x 3 components = 81 operator applies, one ELL slot each);
     the global action is P^T A_loc P with the same halo exchange as the matrix-free operator."""
 
-    def __init__(self, dm, local_apply):
-        self.dm, self.local_apply = dm, local_apply
+    def __init__(self, dm, local_apply, coo=None):
+        """coo (optional): object with .elem_nodes (nelem x 8 local node ids, torch, on dm.device) and
+        .values() -> nelem*576 element-matrix entries (CeedOperatorLinearAssemble layout): the matrix is then
+        assembled from one pass over the Jacobian cache instead of the 81 coloured applies -- same entries up to
+        summation order."""
+        self.dm, self.local_apply, self.coo = dm, local_apply, coo
+        self.coo_dest = None
         N = dm.mesh.nodes_per_dim(1)
         self.N = N
         n = dm.lsize
@@ -357,6 +362,8 @@ class ColoredCoarseMatrix:
     def assemble(self):
         """81 local operator applies (ApplyJacobianCoarse_Ceed without the halo: A_loc itself), then the
         colour slots are re-indexed by neighbour offset: a 27-point block stencil on the node lattice."""
+        if self.coo is not None:
+            return self._assemble_coo()
         for s in range(81):
             self.x.zero_()
             self.x[self.seeds[s]] = 1.0
@@ -364,6 +371,22 @@ class ColoredCoarseMatrix:
             self.vals[s].copy_(self.y)
         self.vals.mul_((self.cols >= 0).to(torch.float64))
         torch.gather(self.vals, 0, self.stencil_src, out=self.svals)
+
+    def _assemble_coo(self):
+        """MatSetValuesCOO stand-in: element-matrix entries summed into the 27-point block stencil."""
+        if self.coo_dest is None:
+            N, n = self.N, self.dm.lsize
+            nodes = self.coo.elem_nodes.long()                                   # (E, 8)
+            ijk = (nodes % N[0], (nodes // N[0]) % N[1], nodes // (N[0] * N[1]))
+            o = 0
+            for d, mul in enumerate((1, 3, 9)):
+                o = o + (ijk[d][:, :, None] - ijk[d][:, None, :] + 1) * mul      # (E, col node, row node)
+            cb = torch.arange(3, device=nodes.device)
+            dest = (o[:, :, None, :, None] * 3 + cb[None, None, :, None, None]) * n \
+                + nodes[:, None, None, :, None] * 3 + cb[None, None, None, None, :]
+            self.coo_dest = dest.reshape(-1).to(torch.int32 if 81 * n < 2 ** 31 else torch.int64)
+        self.svals.zero_()
+        self.svals.view(-1).index_add_(0, self.coo_dest, self.coo.values())
 
     def _build_stencil_map(self):
         """svals[(o*3 + a)][row] = vals[colour(node + d_o)*3 + a][row], o = (dx+1) + 3(dy+1) + 9(dz+1)."""
@@ -408,9 +431,10 @@ class ColoredCoarseMatrix:
 class HMultigrid:
     """Geometric h-multigrid on the assembled p = 1 level: the stand-in for GAMG (elasticity.c:569-585).
 
-    Level 0 is the colouring-assembled p = 1 matrix; every further level halves the element count per
-    axis.  Coarse matrices are Galerkin products A_H = P^T A_h P with trilinear P in index space, assembled
-    by the SAME colouring procedure (81 applications of the rank-local P^T A_h P); one V(2,2) cycle with
+    Level 0 is the assembled p = 1 matrix; every further level halves the element count per
+    axis.  Coarse matrices are Galerkin products A_H = P^T A_h P with trilinear P in index space (on the
+    device: one stencil triple-product kernel per level; on CPU tensors: the colouring procedure applied to
+    the rank-local P^T A_h P -- the same entries); one V(2,2) cycle with
     Chebyshev/Jacobi smoothing is a fixed linear operator, so the outer CG theory holds, and its cost does
     not grow with the mesh the way Jacobi-PCG iterations do.  Brick partitions stay aligned because every
     brick is coarsened in place; the coarsest level is solved by Jacobi-PCG."""
@@ -457,7 +481,11 @@ class HMultigrid:
     def setup(self):
         """after the p = 1 matrix has been assembled: Galerkin levels, diagonals, eigen-estimates"""
         for l in range(1, len(self.dms)):
-            self.mats[l].assemble()
+            m = self.mats[l]
+            if m.svals.is_cuda:  # direct stencil triple product: same entries as colouring P^T A P, one kernel
+                b2(lib.b200_stencil27_galerkin(m.N[0], m.N[1], m.N[2], self.mats[l - 1].svals.data_ptr(), m.svals.data_ptr()))
+            else:
+                m.assemble()
         for l, m in enumerate(self.mats):
             m.diagonal(self.diag[l])
             if l < len(self.mats) - 1:
@@ -562,7 +590,7 @@ class PMultigrid:
         self.r = [mk(l) for l in range(L)]
         self.t = [mk(l) for l in range(L)]
         self.diag = [mk(l) for l in range(L)]
-        self.coarse = ColoredCoarseMatrix(levels[0].dm, levels[0].local_apply)
+        self.coarse = ColoredCoarseMatrix(levels[0].dm, levels[0].local_apply, coo=getattr(levels[0], "coo", None))
         # h_dms: LevelDMs of successively halved meshes below the p = 1 level -> geometric multigrid coarse
         # solve (GAMG stand-in); None -> Jacobi-PCG on the assembled p = 1 matrix
         self.hmg = HMultigrid(V, self.coarse, [levels[0].dm] + list(h_dms)) if h_dms else None

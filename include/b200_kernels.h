@@ -185,6 +185,16 @@ int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P,
                         const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
                         const double *d_jcache, double *d_diag);
 
+/* CeedOperatorLinearAssemble for a trilinear (P = 2) Jacobian level: element matrices straight from the Jacobian
+ * cache, d_values[(e*24 + col)*24 + row], element dof = node*3 + component (node = ix + 2 iy + 4 iz).  Replaces
+ * the 81 coloured operator applications of FormJacobian (misc.c:151-183) by one pass over the cache. */
+int b200_assemble_p1(int problem, const b200_physics *phys, int nelem, int Q, const double *h_interp1d,
+                     const double *h_grad1d, const double *d_jcache, double *d_values);
+
+/* Galerkin product A_H = P^T A_h P of 27-point block stencils (layout of b200_stencil27_spmv) on 2:1 nested
+ * node lattices, fine lattice 2*Nc - 1 per axis, trilinear index-space P (b200_lattice_prolong) */
+int b200_stencil27_galerkin(int Ncx, int Ncy, int Ncz, const double *d_fine, double *d_coarse);
+
 /* p-multigrid transfer (matops.c:115-203): out_L += Eo^T I^(T) Ei in_L, identity QFunction,
  * interpolation Pc -> Pf at the fine GLL points; transpose = 1 is the restriction.
  * d_mult (may be NULL): fine-level inverse multiplicity applied to the fine vector

@@ -170,6 +170,12 @@ CEED_EXTERN int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out
 CEED_EXTERN int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request);
 CEED_EXTERN int CeedOperatorLinearAssembleDiagonal(CeedOperator op, CeedVector assembled, CeedRequest *request);
 CEED_EXTERN int CeedOperatorLinearAssembleAddDiagonal(CeedOperator op, CeedVector assembled, CeedRequest *request);
+/* full assembly in COO form (upstream libCEED >= 0.8; what PETSc's MatSetPreallocationCOO/MatSetValuesCOO consume):
+ * Symbolic returns malloc'ed host arrays the caller frees; values is a CeedVector of num_entries doubles.
+ * /gpu/b200 implements both for fused Jacobian operators on a trilinear (P = 2) level -- the coarse level of the
+ * reference's p-multigrid -- and raises an error otherwise. */
+CEED_EXTERN int CeedOperatorLinearAssembleSymbolic(CeedOperator op, CeedInt *num_entries, CeedInt **rows, CeedInt **cols);
+CEED_EXTERN int CeedOperatorLinearAssemble(CeedOperator op, CeedVector values);
 CEED_EXTERN int CeedOperatorDestroy(CeedOperator *op);
 
 /* ---- /gpu/b200 extensions (not part of upstream; used by the harness and the tests) -- */

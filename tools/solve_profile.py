@@ -48,6 +48,8 @@ def main():
         el.transfers[l].restrict = timed(f"restrict L{l}", el.transfers[l].restrict)
     pc.coarse.assemble = timed("coarse assemble (81 applies)", pc.coarse.assemble)
     pc._coarse_solve = timed("coarse solve", pc._coarse_solve)
+    if pc.hmg is not None:
+        pc.hmg.setup = timed("h-MG setup (Galerkin colouring + eig estimates)", pc.hmg.setup)
     pc.apply = timed("V-cycle total", pc.apply)
     out = el.solve()
     tot = out["time_s"]
