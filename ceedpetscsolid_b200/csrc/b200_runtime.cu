@@ -348,6 +348,81 @@ int b200_fill_strided(double *d, double v, size_t n, size_t stride, size_t count
 }
 int b200_mask_zero(double *d, const int *idx, size_t n) { VEC_KERNEL((k_mask_zero<<<grid_for(n, 256), 256, 0, g_stream>>>(d, idx, n)), n); }
 
+// ---------------------------------------------------------------------------------------------------
+// Host-resident L-vectors (-memtype host, matops.c:40-50): CeedOperatorApply as a three-stage pipeline
+//   copy engine 1: x chunks host -> device | SMs: fused kernel on element chunks | copy engine 2: finished y rows -> host
+// The element range is cut into chunks; chunk c needs the input prefix [0, in_need[c]) and, once its kernel has
+// run, the output prefix [0, out_final[c]) can receive no more contributions (both tables are derived from the
+// offsets by the caller, so ANY numbering is handled correctly; only ordered ones overlap).  PCIe is full duplex,
+// so the apply costs ~max(H2D, D2H) instead of H2D + kernel + D2H.  Both host arrays must be page-locked.
+int b200_host_is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+int b200_apply_hostpipe(int jacobian, int problem, const b200_physics *phys, int nelem, int P, int Q,
+                        const double *hB, const double *hD, const int *d_offsets, const double *d_qa,
+                        double *d_gradu, const double *h_x, double *d_x, double *h_y, double *d_y, size_t lsize,
+                        int nchunks, const int *chunk_end, const size_t *in_need, const size_t *out_final) {
+  enum { MAXC = 64 };
+  static cudaStream_t s_in = nullptr, s_out = nullptr;
+  static cudaEvent_t ev_in[MAXC], ev_k[MAXC], ev_start;
+  if (nchunks < 1 || nchunks > MAXC) return b200::set_error_msg("b200_apply_hostpipe: chunk count out of range");
+  if (!s_in) {
+    B200_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    B200_CHECK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < MAXC; i++) {
+      B200_CHECK(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      B200_CHECK(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+    }
+    B200_CHECK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+  }
+  const int P3 = P * P * P, Q3 = Q * Q * Q;
+  const int nc = jacobian ? b200_jcache_ncomp(problem) : 10;
+  if (nc < 0) return b200::set_error_msg("b200_apply_hostpipe: unknown problem");
+  // everything already queued on the compute stream (zeroing of y, earlier users of x) comes first
+  B200_CHECK(cudaEventRecord(ev_start, g_stream));
+  B200_CHECK(cudaStreamWaitEvent(s_in, ev_start, 0));
+  B200_CHECK(cudaStreamWaitEvent(s_out, ev_start, 0));
+  size_t copied = 0, sent = 0;
+  int e0 = 0;
+  for (int c = 0; c < nchunks; c++) {
+    const bool last = c == nchunks - 1;
+    size_t need = last ? lsize : in_need[c];
+    if (need > lsize) need = lsize;
+    if (need > copied) {
+      B200_CHECK(cudaMemcpyAsync(d_x + copied, h_x + copied, (need - copied) * sizeof(double), cudaMemcpyHostToDevice, s_in));
+      copied = need;
+    }
+    B200_CHECK(cudaEventRecord(ev_in[c], s_in));
+    B200_CHECK(cudaStreamWaitEvent(g_stream, ev_in[c], 0));
+    const int ne = chunk_end[c] - e0;
+    if (ne > 0) {
+      const int rc = jacobian
+          ? b200_apply_jacobian(problem, phys, ne, P, Q, hB, hD, d_offsets + (size_t)e0 * P3, d_qa + (size_t)e0 * nc * Q3, d_x, d_y)
+          : b200_apply_residual(problem, phys, ne, P, Q, hB, hD, d_offsets + (size_t)e0 * P3, d_qa + (size_t)e0 * nc * Q3,
+                                d_gradu ? d_gradu + (size_t)e0 * 9 * Q3 : nullptr, d_x, d_y);
+      if (rc) return rc;
+    }
+    B200_CHECK(cudaEventRecord(ev_k[c], g_stream));
+    B200_CHECK(cudaStreamWaitEvent(s_out, ev_k[c], 0));
+    size_t fin = last ? lsize : out_final[c];
+    if (fin > lsize) fin = lsize;
+    if (fin > sent) {
+      B200_CHECK(cudaMemcpyAsync(h_y + sent, d_y + sent, (fin - sent) * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+      sent = fin;
+    }
+    e0 = chunk_end[c];
+  }
+  B200_CHECK(cudaStreamSynchronize(s_out));  // the libCEED call is synchronous for host-visible results
+  B200_CHECK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
 int b200_elems_per_block(int Q) { return elems_per_block(Q); }
 int b200_strided_layout_q(int elemsize) {
   for (int Q = 2; Q <= 8; Q++)

@@ -22,6 +22,9 @@
 #include "ceed/ceed.h"
 
 #define MAXF 8
+#define B200_PIPE_MAXC 32
+#define B200_PIPE_CHUNKS 16
+#define B200_PIPE_MIN_ELEMS 8192 /* per chunk: enough CTAs to fill the GPU several times over */
 #define CEED_B200_RESOURCE "/gpu/b200"
 
 /* ------------------------------------------------------------------ objects */
@@ -57,6 +60,10 @@ struct CeedElemRestriction_private {
   int strided, backend_strides, layout_q, offsets_borrowed;
   CeedInt strides[3];
   int *d_offsets;
+  /* host-pipeline chunk tables (b200_apply_hostpipe), built on first use; pipe_n = -1: not worth it */
+  int pipe_n, pipe_q;
+  int pipe_end[B200_PIPE_MAXC];
+  size_t pipe_in[B200_PIPE_MAXC], pipe_out[B200_PIPE_MAXC];
 };
 
 struct CeedBasis_private {
@@ -1074,6 +1081,84 @@ static int op_diagonal_generic(CeedOperator op, CeedVector assembled) {
   return 0;
 }
 
+/* Chunk tables for the host pipeline: elements in creation order, chunk boundaries on multiples of the
+ * q-blocked group size; in_need = running max of the highest dof a chunk reads, out_final = lowest dof any
+ * LATER chunk writes.  Any numbering gives correct tables; only (nearly) ordered ones let the stages overlap. */
+static int rstr_pipe_setup(CeedElemRestriction r, int Q) {
+  Ceed ceed = r->ceed;
+  if (r->pipe_n != 0 && r->pipe_q == Q) return 0;
+  r->pipe_q = Q;
+  r->pipe_n = -1;
+  const int EB = b200_elems_per_block(Q);
+  int nch = r->nelem / B200_PIPE_MIN_ELEMS;
+  /* measured on PCIe 5 x16, 2 x 407 MB: 1 chunk 15.9 ms, 4: 11.3, 8: 10.3, 16: 10.25, 32: 10.55 (duplex floor 8.9) */
+  int maxch = B200_PIPE_CHUNKS;
+  const char *env = getenv("CEED_B200_PIPE_CHUNKS"); /* tuning knob; 1 disables the pipeline */
+  if (env && atoi(env) >= 1) maxch = atoi(env) < B200_PIPE_MAXC ? atoi(env) : B200_PIPE_MAXC;
+  if (nch > maxch) nch = maxch;
+  if (nch < 2) return 0;
+  int per = (r->nelem + nch - 1) / nch;
+  per = (per + EB - 1) / EB * EB;
+  const size_t n = (size_t)r->nelem * r->elemsize;
+  int *off = (int *)malloc(n * sizeof(int));
+  if (!off) return CeedError(ceed, 3, "out of memory");
+  B2(ceed, b200_memcpy_d2h(off, r->d_offsets, n * sizeof(int)));
+  const long long span = (long long)(r->ncomp - 1) * r->compstride + 1;
+  int c = 0;
+  long long lo[B200_PIPE_MAXC], hi[B200_PIPE_MAXC];
+  for (int e0 = 0; e0 < r->nelem; e0 += per, c++) {
+    const int e1 = e0 + per < r->nelem ? e0 + per : r->nelem;
+    long long l = r->lsize, h = 0;
+    for (size_t i = (size_t)e0 * r->elemsize; i < (size_t)e1 * r->elemsize; i++) {
+      if (off[i] < l) l = off[i];
+      if (off[i] + span > h) h = off[i] + span;
+    }
+    lo[c] = l; hi[c] = h;
+    r->pipe_end[c] = e1;
+  }
+  free(off);
+  long long run = 0;
+  for (int i = 0; i < c; i++) { if (hi[i] > run) run = hi[i]; r->pipe_in[i] = (size_t)run; }
+  run = r->lsize;
+  for (int i = c - 1; i >= 0; i--) { r->pipe_out[i] = (size_t)run; if (lo[i] < run) run = lo[i]; }
+  r->pipe_n = c;
+  return 0;
+}
+
+/* -memtype host fast path (matops.c:40-50 with host arrays): x current on the host only, y with a host array
+ * attached, both page-locked, one fused operator -> pipelined copies and kernels.  Returns 1 in *done if taken. */
+static int op_apply_hostpipe(CeedOperator op, CeedVector in, CeedVector out, int *done) {
+  Ceed ceed = op->ceed;
+  *done = 0;
+  if (op->kind != OP_FUSED_JACOBIAN && op->kind != OP_FUSED_RESIDUAL) return 0;
+  if (!in || !out || in == out || !in->h_valid || in->d_valid || !in->h || !out->h) return 0;
+  OpField *u = &op->in[0];
+  if (in->length != u->r->lsize || out->length != u->r->lsize) return 0;
+  CeedChk(rstr_pipe_setup(u->r, u->b->Q));
+  if (u->r->pipe_n < 2) return 0;
+  if (!b200_host_is_pinned(in->h) || !b200_host_is_pinned(out->h)) return 0;
+  b200_physics phys;
+  CeedChk(qf_physics(op->qf, &phys));
+  const int jac = op->kind == OP_FUSED_JACOBIAN;
+  const double *qa;
+  double *gu = NULL, *y;
+  if (jac) CeedChk(jcache_get(op, &qa));
+  else {
+    CeedChk(vec_dev_read(op->in[1].v, &qa));
+    if (op->problem != B200_PROB_LINELAS) CeedChk(vec_dev_write(op->out[1].v, &gu));
+  }
+  CeedChk(vec_alloc(in, CEED_MEM_DEVICE));
+  CeedChk(vec_dev_write(out, &y));
+  B2(ceed, b200_vec_set(y, 0.0, (size_t)out->length));
+  B2(ceed, b200_apply_hostpipe(jac, op->problem, &phys, u->r->nelem, u->b->P, u->b->Q, u->b->interp1d, u->b->grad1d,
+                               u->r->d_offsets, qa, gu, in->h, in->d, out->h, y, (size_t)out->length, u->r->pipe_n,
+                               u->r->pipe_end, u->r->pipe_in, u->r->pipe_out));
+  in->d_valid = 1;   /* whole of x was copied on the way */
+  out->h_valid = 1;  /* whole of y is already in the caller's host array */
+  *done = 1;
+  return 0;
+}
+
 int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
   (void)request;
   Ceed ceed = op->ceed;
@@ -1126,6 +1211,11 @@ int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out, CeedReques
     return 0;
   }
   if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  {
+    int done = 0;
+    CeedChk(op_apply_hostpipe(op, in, out, &done));
+    if (done) return 0;
+  }
   for (int i = 0; i < op->qf->nout; i++) {
     CeedVector v = op->out[i].v == CEED_VECTOR_ACTIVE ? out : op->out[i].v;
     if (!v || v == CEED_VECTOR_NONE) continue;

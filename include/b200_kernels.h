@@ -185,6 +185,17 @@ int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P,
                         const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
                         const double *d_jcache, double *d_diag);
 
+/* Host-resident L-vectors (-memtype host; CeedVectorSetArray(HOST) ... TakeArray(HOST), matops.c:40-50): the fused
+ * apply as a pipeline  H2D of x chunks | kernel on element chunks | D2H of finished y rows  on three streams.
+ * chunk_end[c] = one past the last element of chunk c (multiples of b200_elems_per_block(Q) except the last);
+ * in_need[c]   = length of the x prefix chunk c reads;  out_final[c] = length of the y prefix no later chunk touches.
+ * d_y must already be zeroed on the compute stream; h_x, h_y page-locked (b200_host_is_pinned).  Synchronous. */
+int b200_host_is_pinned(const void *p);
+int b200_apply_hostpipe(int jacobian, int problem, const b200_physics *phys, int nelem, int P, int Q,
+                        const double *h_interp1d, const double *h_grad1d, const int *d_offsets, const double *d_qa,
+                        double *d_gradu, const double *h_x, double *d_x, double *h_y, double *d_y, size_t lsize,
+                        int nchunks, const int *chunk_end, const size_t *in_need, const size_t *out_final);
+
 /* CeedOperatorLinearAssemble for a trilinear (P = 2) Jacobian level: element matrices straight from the Jacobian
  * cache, d_values[(e*24 + col)*24 + row], element dof = node*3 + component (node = ix + 2 iy + 4 iz).  Replaces
  * the 81 coloured operator applications of FormJacobian (misc.c:151-183) by one pass over the cache. */

@@ -186,3 +186,37 @@ def test_properties_at_baseline_sizes(G, problem, p, n):
         assert abs(g.jacobian(lvl, e)[i] - d[i]) < 1e-12 * d.max()
     del g
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("problem,p,n,perm", [("hyperFS", 2, (16, 32, 33), None), ("hyperSS", 4, (16, 16, 70), None),
+                                             ("hyperFS", 2, (16, 32, 32), 5), ("linElas", 1, (40, 40, 21), None)])
+def test_host_resident_vectors_take_the_pipelined_path(G, problem, p, n, perm):
+    """-memtype host (matops.c:40-50 with host arrays): page-locked x and y -> chunked H2D | kernel | D2H pipeline.
+    Same numbers as the device-resident apply (atomics reorder: 1e-13), for ordered and for random numberings."""
+    import torch
+    from ceedpetscsolid_b200 import ceed as libceed
+    g = G.GpuProblem(problem, n, p, node_perm_seed=perm)
+    g.residual()
+    lsize = 3 * g.mesh.num_nodes(p)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(lsize)
+    for op in (g.fine.opJacob, g.fine.opApply):
+        xin = x if op is g.fine.opJacob else g.u_fine
+        ref = g.apply(op, xin, lsize)
+        for pinned in (True, False):
+            xh = torch.from_numpy(xin.copy())
+            yh = torch.full((lsize,), np.nan, dtype=torch.float64)
+            if pinned:
+                xh, yh = xh.pin_memory(), yh.pin_memory()
+            xc, yc = g.ceed.Vector(lsize), g.ceed.Vector(lsize)
+            xc.set_array(xh, libceed.MEM_HOST)
+            yc.set_array(yh, libceed.MEM_HOST)
+            n0 = libceed.launch_count()
+            op.apply(xc, yc)
+            launches = libceed.launch_count() - n0
+            xc.take_array(libceed.MEM_HOST)
+            yc.take_array(libceed.MEM_HOST)
+            assert (launches >= 2) == pinned, launches    # one kernel per element chunk vs a single kernel
+            assert rel_err(yh.numpy(), ref) < 1e-13
+            # x is current on the device afterwards: a second, device-side use must not need the host copy
+            xc.destroy(); yc.destroy()
