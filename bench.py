@@ -129,7 +129,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                  clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1 * lengths[2], 0, 0, 1, 0]})
     gmesh = BoxMesh(n=n, perturb=app.perturb, seed=0, lengths=lengths)
     el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank, gmesh=gmesh,
-                    coarse_rtol=args.coarse_rtol, coarse=args.coarse, assemble=args.assemble)
+                    coarse_rtol=args.coarse_rtol, coarse=args.coarse, assemble=args.assemble, masked=args.dm == "masked")
     el.pc.coarse_maxit = args.coarse_maxit
     libceed.launch_count_reset()
     sampler = ClockSampler(local_rank)
@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--load-steps", type=int, default=10)
     ap.add_argument("--coarse-rtol", type=float, default=1e-2)
     ap.add_argument("--coarse-maxit", type=int, default=500)
+    ap.add_argument("--dm", default="masked", choices=["masked", "compressed"],
+                    help="global-vector layout of the DM stand-in (matops.LevelDM)")
     ap.add_argument("--assemble", default="coo", choices=["coo", "color"], help="p=1 matrix: CeedOperatorLinearAssemble element matrices, or 81 coloured applies (misc.c:151-183)")
     ap.add_argument("--coarse", default="hmg", choices=["hmg", "pcg"], help="coarse solve on the assembled p=1 level: h-multigrid (GAMG stand-in) or Jacobi-PCG")
     args = ap.parse_args()
@@ -237,7 +239,10 @@ def main():
         from ceedpetscsolid_b200.halo import Halo
         halo = Halo(gmesh, grid, rank, p, dist)
     # N > 1: shared-dof global vectors -> one symmetric sum-and-share halo exchange per MatMult
-    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=True)
+    masked = args.dm == "masked"
+    config["dm"] = ("masked constrained dofs: Krylov vectors have the L-vector layout, no G2L/L2G copies" if masked
+                    else "compressed global vectors: G2L gather + L2G scatter around every apply (PETSc DM style)")
+    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=True, masked=masked)
     user = matops.setup_jacobian_ctx(dm, ceed, data[fine], phys)
 
     # state: smooth admissible displacement -> residual fills gradu
@@ -250,6 +255,7 @@ def main():
     del u, r
     X, Y = dm.create_global_vector(), dm.create_global_vector()
     X.copy_(torch.from_numpy(np.random.default_rng(1 + rank).standard_normal(dm.nglobal)))
+    dm.zero_constrained(X)
 
     def barrier():
         if world > 1:

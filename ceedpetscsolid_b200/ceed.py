@@ -132,6 +132,7 @@ _proto("b200_scatter_set", _vp, _vp, _vp, _sz)
 _proto("b200_scatter_add", _vp, _vp, _vp, _sz)
 _proto("b200_mask_zero", _vp, _vp, _sz)
 _proto("b200_gather_or_zero", _vp, _vp, _vp, _sz)
+_proto("b200_copy_where", _vp, _vp, _vp, _sz)
 _proto("b200_ell_spmv", _sz, _i, _vp, _vp, _vp, _vp)
 _proto("b200_vec_axpy_dev", _vp, _vp, _sz, _vp, _vp, _d)
 _proto("b200_vec_aypx_dev", _vp, _vp, _sz, _vp, _vp)

@@ -46,6 +46,9 @@ __global__ void k_scatter_add(double *dst, const int *idx, const double *src, si
 __global__ void k_gather_or_zero(double *dst, const double *src, const int *idx, size_t n) {
   GRID_STRIDE(i, n) { const int j = idx[i]; dst[i] = j >= 0 ? src[j] : 0.0; }
 }
+__global__ void k_copy_where(double *dst, const double *src, const int *idx, size_t n) {
+  GRID_STRIDE(i, n) { const int j = idx[i]; if (j >= 0) dst[i] = src[j]; }
+}
 // BLAS-1 with DEVICE scalars (alpha = sign * num[0] / den[0]): lets a Krylov loop run without host syncs
 __global__ void k_axpy_dev(double *y, const double *x, size_t n, const double *num, const double *den, double sign) {
   const double a = sign * num[0] / den[0];
@@ -312,6 +315,7 @@ int b200_gather(double *dst, const double *src, const int *idx, size_t n) { VEC_
 int b200_scatter_set(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_set<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
 int b200_scatter_add(double *dst, const int *idx, const double *src, size_t n) { VEC_KERNEL((k_scatter_add<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, idx, src, n)), n); }
 int b200_gather_or_zero(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_gather_or_zero<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
+int b200_copy_where(double *dst, const double *src, const int *idx, size_t n) { VEC_KERNEL((k_copy_where<<<grid_for(n, 256), 256, 0, g_stream>>>(dst, src, idx, n)), n); }
 int b200_vec_axpy_dev(double *y, const double *x, size_t n, const double *num, const double *den, double sign) {
   VEC_KERNEL((k_axpy_dev<<<grid_for(n, 256), 256, 0, g_stream>>>(y, x, n, num, den, sign)), n);
 }

@@ -61,7 +61,7 @@ class AppCtx:
     clamp: dict = field(default_factory=lambda: {(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
 
 
-def build_h_dms(gmesh, grid, rank, world, faces, device, dist=None, min_elems=2):
+def build_h_dms(gmesh, grid, rank, world, faces, device, dist=None, min_elems=2, masked=False):
     """LevelDMs (degree 1) of successively halved box meshes below the p = 1 level, for the h-multigrid coarse
     solve.  Halving stops when a brick would have an odd element count or fewer than `min_elems` per axis."""
     dms = []
@@ -74,7 +74,7 @@ def build_h_dms(gmesh, grid, rank, world, faces, device, dist=None, min_elems=2)
         if world > 1:
             from .halo import Halo
             halo = Halo(gm, grid, rank, 1, dist, device=device if isinstance(device, str) and device == "cpu" else None)
-        dms.append(matops.LevelDM(mesh, 1, bc_faces=faces, halo=halo, device=device, shared=True))
+        dms.append(matops.LevelDM(mesh, 1, bc_faces=faces, halo=halo, device=device, shared=True, masked=masked))
     return dms
 
 
@@ -153,7 +153,9 @@ class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
     def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg",
-                 assemble="coo"):
+                 assemble="coo", masked=True):
+        """masked: constrained dofs are masked in L-vector-shaped global vectors (no G2L/L2G copies, see LevelDM);
+        False: compressed PETSc-style global vectors."""
         self.app, self.dist = app, dist
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
@@ -170,7 +172,8 @@ class Elasticity:
             if world > 1:
                 from .halo import Halo
                 halo = Halo(self.gmesh, grid, rank, deg, dist)
-            dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}", shared=True)
+            dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}", shared=True,
+                                masked=masked)
             self.dms.append(dm)
             self.users.append(matops.setup_jacobian_ctx(dm, self.ceed, self.data[l], self.phys))
         fine = len(self.degrees) - 1
@@ -201,14 +204,12 @@ class Elasticity:
             self.levels[fine].forcing = Fext
         self.V = solver.Vec(dist if world > 1 else None)
         self.V.consistent = {}
-        for dm in self.dms:
+        h_dms = build_h_dms(self.gmesh, grid, rank, world, faces, f"cuda:{device_id}", dist, masked=masked) \
+            if coarse == "hmg" else None
+        for dm in self.dms + list(h_dms or []):
             if dm.dot_weight is not None:
                 self.V.weights[dm.nglobal] = dm.dot_weight
-                self.V.consistent[dm.nglobal] = dm.make_consistent
-        h_dms = build_h_dms(self.gmesh, grid, rank, world, faces, f"cuda:{device_id}", dist) if coarse == "hmg" else None
-        for dm in (h_dms or []):
-            if dm.dot_weight is not None:
-                self.V.weights[dm.nglobal] = dm.dot_weight
+            if dm.dot_weight is not None or dm.masked:
                 self.V.consistent[dm.nglobal] = dm.make_consistent
         self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol, h_dms=h_dms)
         self.U = self.dms[fine].create_global_vector()
@@ -253,13 +254,13 @@ class Elasticity:
         true_l = setuplibceed.setup_true_solution(self.ceed, self.mesh, self.data[fine], self.degrees[fine] + 1)
         dm = self.dms[fine]
         tg = torch.from_numpy(true_l).to(dm.device)[dm.free_owned_idx.long()]
+        dm.zero_constrained(tg)
         err2, u2 = self.V.dot(self.U - tg, self.U - tg), self.V.dot(self.U, self.U)
         return math.sqrt(err2 / u2)
 
     def _global_unconstrained(self):
         dm = self.dms[-1]
-        local = float(dm.dot_weight.sum().item()) if dm.dot_weight is not None else float(dm.nglobal)
-        n = torch.tensor([local], dtype=torch.float64, device=dm.device)
+        n = torch.tensor([dm.n_unconstrained_local], dtype=torch.float64, device=dm.device)
         if self.dist is not None and self.dist.get_world_size() > 1:
             self.dist.all_reduce(n)
         return int(round(n.item()))

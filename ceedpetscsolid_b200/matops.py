@@ -28,13 +28,21 @@ class LevelDM:
     or None.  `halo`: a ceedpetscsolid_b200.halo.Halo for partitioned runs, else None.
     """
 
-    def __init__(self, mesh, degree, bc_faces="all", halo=None, device="cuda", node_perm=None, shared=False):
-        """shared=True (partitioned runs): "global" vectors keep a consistent copy of every interface dof on
+    def __init__(self, mesh, degree, bc_faces="all", halo=None, device="cuda", node_perm=None, shared=False,
+                 masked=False):
+        """masked=True: "global" vectors have the LOCAL layout (every local dof, interface copies included) and the
+        Dirichlet dofs are carried along as entries that are always exactly zero -- rows and columns of constrained
+        dofs are masked instead of compressed out.  DMGlobalToLocal / DMLocalToGlobal then move no data at all: the
+        operator reads X and accumulates into Y directly (one small kernel zeroes the Dirichlet rows of Y), which
+        removes two full passes over the vectors from every MatMult.  Krylov iterates are unchanged: zero entries
+        do not contribute to inner products and stay zero under the masked operator, Jacobi and the transfers.
+        shared=True (partitioned runs): "global" vectors keep a consistent copy of every interface dof on
         every rank that holds it, so DMGlobalToLocal needs no communication and DMLocalToGlobal(ADD) is ONE
         symmetric sum-and-share exchange instead of two one-directional ones; `dot_weight` (1/#ranks holding
         the dof) makes inner products count each dof once."""
         self.mesh, self.degree, self.halo = mesh, degree, halo
-        self.shared = bool(shared and halo is not None)
+        self.masked = bool(masked)
+        self.shared = bool((shared or masked) and halo is not None)
         self.device = torch.device(device)
         nn = mesh.num_nodes(degree)
         self.lsize = 3 * nn
@@ -46,19 +54,22 @@ class LevelDM:
             bc = np.zeros(nn, bool); bc[node_perm] = bc_nodes
             free_owned, bc_nodes = fo, bc
         self.bc_nodes = bc_nodes
-        fo_idx = np.flatnonzero(np.repeat(free_owned, 3)).astype(np.int32)
+        free_idx = np.flatnonzero(np.repeat(free_owned, 3)).astype(np.int32)
         bc_idx = np.flatnonzero(np.repeat(bc_nodes, 3)).astype(np.int32)
+        fo_idx = np.arange(self.lsize, dtype=np.int32) if self.masked else free_idx
         self.nglobal = fo_idx.size
         self.free_owned_idx = torch.from_numpy(fo_idx).to(self.device)
         l2g = np.full(self.lsize, -1, dtype=np.int32)  # local dof -> global dof (-1: ghost or Dirichlet)
-        l2g[fo_idx] = np.arange(fo_idx.size, dtype=np.int32)
+        l2g[free_idx] = free_idx if self.masked else np.arange(free_idx.size, dtype=np.int32)
         self.local_to_global_idx = torch.from_numpy(l2g).to(self.device)
         self.dot_weight = None
+        self.n_unconstrained_local = float(free_idx.size)  # this rank's share of the global unconstrained dofs
         if self.shared:
-            w = np.repeat(1.0 / halo.rank_multiplicity, 3)[fo_idx]
-            self.dot_weight = torch.from_numpy(w).to(self.device)
+            w = np.repeat(1.0 / halo.rank_multiplicity, 3)
+            self.n_unconstrained_local = float(w[free_idx].sum())
+            self.dot_weight = torch.from_numpy(w[fo_idx]).to(self.device)
         self.bc_idx = torch.from_numpy(bc_idx).to(self.device)
-        self._fo_host, self._bc_host = fo_idx, bc_idx
+        self._fo_host, self._bc_host, self._free_host = fo_idx, bc_idx, free_idx
 
     # ---- Vec creation (DMCreateGlobalVector / DMCreateLocalVector)
     def create_global_vector(self, mem=MEM_DEVICE):
@@ -72,7 +83,28 @@ class LevelDM:
                            pin_memory=(mem == MEM_HOST and torch.cuda.is_available()))
 
     # ---- DMGlobalToLocal(INSERT_VALUES) / DMLocalToGlobal(ADD_VALUES) (matops.c:33,57)
+    def zero_constrained(self, X):
+        """masked layouts: zero the Dirichlet entries of a "global" vector (no-op otherwise: they are not stored)"""
+        if not self.masked or self.bc_idx.numel() == 0:
+            return
+        if X.is_cuda:
+            b2(lib.b200_mask_zero(X.data_ptr(), self.bc_idx.data_ptr(), self.bc_idx.numel()))
+        else:
+            X.numpy()[self._bc_host] = 0.0
+
+    def fix_diagonal(self, D):
+        """masked layouts: unit diagonal on the Dirichlet rows (the masked operator has zero rows there)"""
+        if not self.masked or self.bc_idx.numel() == 0:
+            return
+        D[self.bc_idx.long()] = 1.0
+
     def global_to_local(self, X, Xloc):
+        if self.masked:       # free dofs only: the Dirichlet entries of Xloc (boundary values) are left alone
+            if Xloc.is_cuda:
+                b2(lib.b200_copy_where(Xloc.data_ptr(), X.data_ptr(), self.local_to_global_idx.data_ptr(), self.lsize))
+            else:
+                Xloc.numpy()[self._free_host] = X.numpy()[self._free_host]
+            return
         if Xloc.is_cuda:
             b2(lib.b200_scatter_set(Xloc.data_ptr(), self.free_owned_idx.data_ptr(), X.data_ptr(), self.nglobal))
         else:
@@ -98,6 +130,11 @@ class LevelDM:
                 self.halo.sum_and_share(Yloc)
             else:
                 self.halo.ghost_to_owner_add(Yloc)
+        if self.masked:
+            if Y.data_ptr() != Yloc.data_ptr():
+                Y.copy_(Yloc)
+            self.zero_constrained(Y)
+            return
         if Yloc.is_cuda:
             b2(lib.b200_gather(Y.data_ptr(), Yloc.data_ptr(), self.free_owned_idx.data_ptr(), self.nglobal))
         else:
@@ -106,6 +143,7 @@ class LevelDM:
     def make_consistent(self, X):
         """shared layouts: replace every copy of an interface dof by the average of the copies"""
         if not self.shared:
+            self.zero_constrained(X)
             return
         Xl = self.create_local_vector(MEM_DEVICE if X.is_cuda else MEM_HOST)
         X.mul_(self.dot_weight)
@@ -150,6 +188,17 @@ def setup_jacobian_ctx(dm, ceed, data, phys, physSmoother=None, memType=MEM_DEVI
 def ApplyLocalCeedOp(X, Y, user, zero_xloc=False):
     """matops.c:26-60: Y = P^T A_loc P X.  zero_xloc fuses the caller's VecZeroEntries(Xloc)
     (ApplyJacobian_Ceed, matops.c:106) into the global-to-local pass."""
+    dm = user.dm
+    if dm.masked and zero_xloc:
+        # masked layout: X already IS the L-vector with zero boundary values and Y the L-vector to accumulate
+        # into -- no DMGlobalToLocal / DMLocalToGlobal data movement at all
+        user.Xceed.set_array(X, user.memType, USE_POINTER)
+        user.Yceed.set_array(Y, user.memType, USE_POINTER)
+        user.op.apply(user.Xceed, user.Yceed)
+        user.Xceed.take_array(user.memType)
+        user.Yceed.take_array(user.memType)
+        dm.local_to_global(Y, Y)        # halo sum-and-share (partitioned runs) + zero the Dirichlet rows, in place
+        return
     if zero_xloc:
         user.dm.zero_and_global_to_local(X, user.Xloc)            # :106 + :33
     else:
@@ -187,6 +236,7 @@ def GetDiag_Ceed(user, D):
         user.qf.set_context(user.phys)
     user.Xceed.take_array(user.memType)
     user.dm.local_to_global(user.Xloc, D)
+    user.dm.fix_diagonal(D)
     user.Xloc.zero_()
 
 

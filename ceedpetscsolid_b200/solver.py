@@ -415,6 +415,10 @@ class ColoredCoarseMatrix:
 
     def mult(self, X, Y):
         dm = self.dm
+        if dm.masked:  # X is the L-vector with zero Dirichlet entries already
+            self.local_mult(X, Y)
+            dm.local_to_global(Y, Y)
+            return
         dm.zero_and_global_to_local(X, self.Xloc)
         self.local_mult(self.Xloc, self.Yloc)
         dm.local_to_global(self.Yloc, Y)
@@ -426,6 +430,7 @@ class ColoredCoarseMatrix:
         slot = 13 * 3 + (rows % 3)                       # centre neighbour (dx=dy=dz=0), same component
         self.Yloc.copy_(self.svals[slot, rows])
         self.dm.local_to_global(self.Yloc, D)
+        self.dm.fix_diagonal(D)
 
 
 class HMultigrid:

@@ -91,6 +91,8 @@ int b200_mask_zero(double *d, const int *idx, size_t n);                        
 /* VecZeroEntries(Xloc) + DMGlobalToLocal(INSERT) in one pass (matops.c:106,33):
  * dst[i] = idx[i] >= 0 ? src[idx[i]] : 0  (idx = local dof -> global dof, -1 for ghost / Dirichlet dofs) */
 int b200_gather_or_zero(double *dst, const double *src, const int *idx, size_t n);
+/* dst[i] = src[idx[i]] where idx[i] >= 0, dst[i] untouched elsewhere (masked layouts: free dofs only) */
+int b200_copy_where(double *dst, const double *src, const int *idx, size_t n);
 /* BLAS-1 with DEVICE scalars (alpha = sign * num[0] / den[0]) and a fused CG update
  *   x += alpha p,  r -= alpha Ap,  z = dinv .* r   (alpha = rz[0] / pAp[0])
  * so that a Krylov loop (the coarse-level solve) runs without a host synchronisation per dot product */

@@ -32,8 +32,9 @@ def main():
     degrees, data, phys = setuplibceed.setup_all(ceed, mesh, problem, p)
     fine = len(degrees) - 1
     halo = Halo(gmesh, grid, rank, p, dist)
-    shared = os.environ.get("MGPU_SHARED", "0") == "1"
-    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=shared)
+    shared = os.environ.get("MGPU_SHARED", "0") in ("1", "masked")
+    masked = os.environ.get("MGPU_SHARED", "0") == "masked"
+    dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=shared, masked=masked)
     user = matops.setup_jacobian_ctx(dm, ceed, data[fine], phys)
     u = torch.from_numpy(smooth_displacement(mesh.node_coords(p)).reshape(-1)).cuda()
     uc, rc = ceed.Vector(u.numel()), ceed.Vector(u.numel())
@@ -72,8 +73,9 @@ def main():
             seen[d] += 1
         free = ~gbc
         err = rel_err(ypar[free], yref[free])
-        ok = bool(np.all(seen[free] >= 1) and (shared or np.all(seen[free] == 1)) and np.all(seen[gbc] == 0) and err < 1e-12)
-        print(f"mgpu_check world={world} bricks={grid} shared={shared}: rel err {err:.2e} -> {'PASS' if ok else 'FAIL'}")
+        ok = bool(np.all(seen[free] >= 1) and (shared or np.all(seen[free] == 1)) and err < 1e-12
+                  and (np.all(ypar[gbc] == 0.0) if masked else np.all(seen[gbc] == 0)))
+        print(f"mgpu_check world={world} bricks={grid} shared={shared} masked={masked}: rel err {err:.2e} -> {'PASS' if ok else 'FAIL'}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

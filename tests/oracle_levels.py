@@ -10,8 +10,8 @@ from oracle import oracle
 
 
 class OracleShared:
-    def __init__(self, app):
-        self.app = app
+    def __init__(self, app, masked=False):
+        self.app, self.masked = app, masked
         self.mesh = BoxMesh(n=app.n, perturb=app.perturb, seed=0)
         self.degrees = setuplibceed.level_degrees(app.degree, app.multigrid)
         p = app.degree
@@ -30,7 +30,7 @@ class OracleLevel:
         self.P = self.deg + 1
         self.B, self.D, _, _ = oracle.basis_1d(self.P, sh.Q, 0)
         self.off = mesh.offsets(self.deg)
-        self.dm = matops.LevelDM(mesh, self.deg, bc_faces=list(app.clamp.keys()), device="cpu")
+        self.dm = matops.LevelDM(mesh, self.deg, bc_faces=list(app.clamp.keys()), device="cpu", masked=sh.masked)
         self.n, self.device = self.dm.nglobal, self.dm.device
         self.Xloc, self.Yloc = self.dm.create_local_vector(matops.MEM_HOST), self.dm.create_local_vector(matops.MEM_HOST)
         self.bc_values = Elasticity._bc_values_fn(self.dm, app) if is_fine else None
@@ -51,6 +51,7 @@ class OracleLevel:
         d = oracle.operator_diagonal(sh.app.problem, sh.phys, sh.mesh.nelem, self.P, sh.Q, self.B, self.D, self.off,
                                      sh.qdata, sh.gradu, self.dm.lsize)
         self.dm.local_to_global(torch.from_numpy(d), D)
+        self.dm.fix_diagonal(D)
 
     def bc_increment_rhs(self, F, load_prev, load):
         self.Xloc.zero_()
@@ -91,15 +92,19 @@ class OracleTransfer:
         self.c.dm.local_to_global(torch.from_numpy(y), Yc)
 
 
-def oracle_solve(app, log=None, coarse="hmg", **kw):
+def oracle_solve(app, log=None, coarse="hmg", masked=True, **kw):
     from ceedpetscsolid_b200.elasticity import build_h_dms
-    sh = OracleShared(app)
+    sh = OracleShared(app, masked)
     L = len(sh.degrees)
     levels = [OracleLevel(sh, l, l == L - 1) for l in range(L)]
     transfers = [None] + [OracleTransfer(sh, levels[l - 1], levels[l]) for l in range(1, L)]
     V = solver.Vec(None)
+    V.consistent = {}
     faces = "all" if app.test_mode else list(app.clamp.keys())
-    h_dms = build_h_dms(sh.mesh, (1, 1, 1), 0, 1, faces, "cpu") if coarse == "hmg" else None
+    h_dms = build_h_dms(sh.mesh, (1, 1, 1), 0, 1, faces, "cpu", masked=masked) if coarse == "hmg" else None
+    if masked:
+        for dm in [lev.dm for lev in levels] + list(h_dms or []):
+            V.consistent[dm.nglobal] = dm.make_consistent
     pc = solver.PMultigrid(V, levels, transfers, h_dms=h_dms)
     U = levels[-1].dm.create_global_vector(matops.MEM_HOST)
     out = solver.newton_solve(V, levels[-1], pc, U, num_increments=app.num_steps, log=log, **kw)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("shared", ["0", "1"])
+@pytest.mark.parametrize("shared", ["0", "1", "masked"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_jacobian_matches_oracle(world, shared):
     import torch

@@ -110,3 +110,63 @@ def test_partitioned_apply_matches_serial(tmp_path, world, n, p):
     np.testing.assert_allclose(holders, 1.0, atol=1e-14)
     assert np.linalg.norm(ypar - yser) < 1e-13 * np.linalg.norm(yser)
     assert mult_ser.min() >= 1
+
+
+def _masked_worker(rank, world, port, n, p, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ceedpetscsolid_b200 import matops, solver
+        from helpers import PHYS
+        from oracle import oracle
+        grid = grid_for(world)
+        gmesh = BoxMesh(n=n, perturb=0.08, seed=0)
+        brick = gmesh.brick(grid, rank) if world > 1 else gmesh
+        halo = Halo(gmesh, grid, rank, p, dist, device="cpu") if world > 1 else None
+        dm = matops.LevelDM(brick, p, bc_faces=[(0, 0)], halo=halo, device="cpu", masked=True)
+        assert dm.nglobal == dm.lsize and dm.shared == (world > 1)
+        gid = _global_node_ids(gmesh, brick, p)
+        gdof = (gid[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+        P = Q = p + 1
+        B, D, _, _ = oracle.basis_1d(P, Q, 0)
+        qdata = oracle.setup_geo(brick.nelem, Q, brick.offsets(1), brick.coord_lvector())
+
+        def A(X, Y):  # masked MatMult: X is the L-vector itself; one sum-and-share, then the Dirichlet rows are zeroed
+            Y.copy_(torch.from_numpy(oracle.operator_apply("linElas", True, PHYS, brick.nelem, P, Q, B, D, brick.offsets(p),
+                                                           qdata, None, X.numpy())))
+            dm.local_to_global(Y, Y)
+
+        V = solver.Vec(dist if world > 1 else None)
+        if dm.dot_weight is not None:
+            V.weights[dm.nglobal] = dm.dot_weight
+        b = torch.from_numpy(np.random.default_rng(9).standard_normal(gmesh.lsize(p))[gdof].copy())
+        dm.zero_constrained(b)
+        x = torch.zeros_like(b)
+        its, reason, rn = solver.pcg(V, A, b, x, rtol=1e-10, maxit=500)
+        nrm2 = V.dot(x, x)
+        np.savez(os.path.join(out, f"m{world}_{rank}.npz"), gdof=gdof, x=x.numpy(), its=its, nrm2=nrm2,
+                 nfree=dm.n_unconstrained_local)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_masked_layout_partitioned_cg_matches_serial(tmp_path):
+    """masked LevelDM (L-vector-shaped Krylov vectors, Dirichlet rows zeroed, interface copies weighted in dots):
+    2 ranks and 1 rank solve the same clamped problem to the same solution in the same number of CG steps (+-rounding)."""
+    n, p = (4, 2, 2), 2
+    res = {}
+    for world in (1, 2):
+        port = _free_port()
+        mp.spawn(_masked_worker, args=(world, port, n, p, str(tmp_path)), nprocs=world, join=True)
+        res[world] = [np.load(tmp_path / f"m{world}_{r}.npz") for r in range(world)]
+    ser = res[1][0]
+    xs = np.zeros(ser["gdof"].max() + 1)
+    xs[ser["gdof"]] = ser["x"]
+    assert int(ser["its"]) > 5
+    nfree = sum(float(d["nfree"]) for d in res[2])
+    assert abs(nfree - float(ser["nfree"])) < 1e-9          # every unconstrained dof counted once across ranks
+    for d in res[2]:
+        assert abs(int(d["its"]) - int(ser["its"])) <= 3   # unpreconditioned CG, ~300 its: summation order moves the last step
+        assert abs(float(d["nrm2"]) - float(ser["nrm2"])) < 1e-8 * float(ser["nrm2"])
+        assert np.linalg.norm(d["x"] - xs[d["gdof"]]) < 1e-7 * np.linalg.norm(xs)
