@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--coarse-maxit", type=int, default=500)
     ap.add_argument("--dm", default="masked", choices=["masked", "compressed"],
                     help="global-vector layout of the DM stand-in (matops.LevelDM)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not overlap the halo exchange with the interior elements")
     ap.add_argument("--assemble", default="coo", choices=["coo", "color"], help="p=1 matrix: CeedOperatorLinearAssemble element matrices, or 81 coloured applies (misc.c:151-183)")
     ap.add_argument("--coarse", default="hmg", choices=["hmg", "pcg"], help="coarse solve on the assembled p=1 level: h-multigrid (GAMG stand-in) or Jacobi-PCG")
     args = ap.parse_args()
@@ -190,7 +191,8 @@ def main():
                 else f"{problem} degree {p} Jacobian MatMult, box {args.n}^3 sharded")
     config = {"workload": workload, "problem": problem, "degree": p, "levels": "fine level of {1,2,4}",
               "elements_per_gpu": None, "scatter": "fp64 atomics", "l2": "inputs larger than L2 (no flush needed)",
-              "bricks": None, "halo": "none (1 GPU)" if world == 1 else "NCCL p2p, one sum-and-share exchange per MatMult"}
+              "bricks": None, "halo": "none (1 GPU)" if world == 1 else "NCCL p2p, one sum-and-share exchange per MatMult" + (
+                  "" if (args.no_overlap or args.dm != "masked") else ", overlapped with the interior elements")}
 
     # ------------------------------------------------------------------ CPU reference arm
     if args.impl == "reference":
@@ -227,7 +229,7 @@ def main():
                         lengths=tuple(float(g) for g in grid))  # the domain grows with the mesh: cubic elements
     else:
         gmesh = BoxMesh(n=(args.n,) * 3, perturb=0.08, seed=0)
-    mesh = gmesh.brick(grid, rank) if world > 1 else gmesh
+    mesh = gmesh.brick(grid, rank, interface_first=args.dm == "masked" and not args.no_overlap) if world > 1 else gmesh
     config["elements_per_gpu"] = mesh.nelem
     config["bricks"] = "x".join(map(str, grid))
 

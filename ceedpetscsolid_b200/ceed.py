@@ -105,6 +105,7 @@ _proto("CeedOperatorLinearAssembleSymbolic", _vp, C.POINTER(_i), C.POINTER(C.POI
 _proto("CeedOperatorLinearAssemble", _vp, _vp)
 _proto("CeedOperatorDestroy", _pvp)
 _proto("CeedOperatorIsFusedB200", _vp, C.POINTER(_i))
+_proto("CeedOperatorApplyAddRangeB200", _vp, _vp, _vp, _i, _i)
 _proto("CeedB200LaunchCount", restype=C.c_ulonglong)
 _proto("CeedB200LaunchCountReset", restype=None)
 _proto("CeedB200SetStream", _vp, _vp)
@@ -429,6 +430,9 @@ class Operator(_Obj):
 
     def apply_add(self, u, v):
         self._chk(lib.CeedOperatorApplyAdd(self.h, u.h, v.h, REQUEST_IMMEDIATE))
+
+    def apply_add_range(self, u, v, start, stop):
+        self._chk(lib.CeedOperatorApplyAddRangeB200(self.h, u.h, v.h, int(start), int(stop)))
 
     def linear_assemble_diagonal(self, assembled):
         self._chk(lib.CeedOperatorLinearAssembleDiagonal(self.h, assembled.h, REQUEST_IMMEDIATE))

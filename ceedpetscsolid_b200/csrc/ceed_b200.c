@@ -1159,6 +1159,43 @@ static int op_apply_hostpipe(CeedOperator op, CeedVector in, CeedVector out, int
   return 0;
 }
 
+/* fused residual / Jacobian kernels on the element range [e0, e1): e0 a multiple of the q-blocked group size */
+static int op_apply_fused_range(CeedOperator op, CeedVector in, CeedVector out, int e0, int e1) {
+  Ceed ceed = op->ceed;
+  const double *x;
+  double *y;
+  OpField *u = &op->in[0];
+  b200_physics phys;
+  CeedChk(qf_physics(op->qf, &phys));
+  const int P = u->b->P, Q = u->b->Q, P3 = P * P * P, Q3 = Q * Q * Q;
+  if (in->length < u->r->lsize || out->length < u->r->lsize)
+    return CeedError(ceed, 1, "operator %s: active vectors shorter than the restriction's L-vector size %d", op->qf->name, u->r->lsize);
+  const int *off = u->r->d_offsets + (size_t)e0 * P3;
+  if (op->kind == OP_FUSED_JACOBIAN) {
+    const double *jc;
+    CeedChk(jcache_get(op, &jc));
+    CeedChk(vec_dev_read(in, &x));
+    CeedChk(vec_dev_rw(out, &y));
+    B2(ceed, b200_apply_jacobian(op->problem, &phys, e1 - e0, P, Q, u->b->interp1d, u->b->grad1d, off,
+                                 jc + (size_t)e0 * b200_jcache_ncomp(op->problem) * Q3, x, y));
+  } else {
+    const double *qd;
+    double *gu = NULL;
+    CeedChk(vec_dev_read(op->in[1].v, &qd));
+    if (op->problem != B200_PROB_LINELAS) {
+      /* a partial range rewrites only its own slice of gradu: the rest must stay valid */
+      if (e0 == 0 && e1 == u->r->nelem) CeedChk(vec_dev_write(op->out[1].v, &gu));
+      else CeedChk(vec_dev_rw(op->out[1].v, &gu));
+      gu += (size_t)e0 * 9 * Q3;
+    }
+    CeedChk(vec_dev_read(in, &x));
+    CeedChk(vec_dev_rw(out, &y));
+    B2(ceed, b200_apply_residual(op->problem, &phys, e1 - e0, P, Q, u->b->interp1d, u->b->grad1d, off,
+                                 qd + (size_t)e0 * 10 * Q3, gu, x, y));
+  }
+  return 0;
+}
+
 int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
   (void)request;
   Ceed ceed = op->ceed;
@@ -1168,9 +1205,9 @@ int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedReq
   }
   if (op->kind == OP_UNSET) CeedChk(op_setup(op));
   if (op->kind == OP_GENERIC) return op_apply_generic(op, in, out);
-  const double *x;
-  double *y;
   if (op->kind == OP_FUSED_TRANSFER) {
+    const double *x;
+    double *y;
     const int prolong = op->qf->in[0].emode == CEED_EVAL_INTERP;
     OpField *c = prolong ? &op->in[0] : &op->out[0], *f = prolong ? &op->out[0] : &op->in[0];
     CeedChk(vec_dev_read(in, &x));
@@ -1179,28 +1216,25 @@ int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedReq
                                  NULL, x, y));
     return 0;
   }
-  OpField *u = &op->in[0];
-  b200_physics phys;
-  CeedChk(qf_physics(op->qf, &phys));
-  const int nelem = u->r->nelem, P = u->b->P, Q = u->b->Q;
-  if (in->length < u->r->lsize || out->length < u->r->lsize)
-    return CeedError(ceed, 1, "operator %s: active vectors shorter than the restriction's L-vector size %d", op->qf->name, u->r->lsize);
-  if (op->kind == OP_FUSED_JACOBIAN) {
-    const double *jc;
-    CeedChk(jcache_get(op, &jc));
-    CeedChk(vec_dev_read(in, &x));
-    CeedChk(vec_dev_rw(out, &y));
-    B2(ceed, b200_apply_jacobian(op->problem, &phys, nelem, P, Q, u->b->interp1d, u->b->grad1d, u->r->d_offsets, jc, x, y));
-  } else {
-    const double *qd;
-    double *gu = NULL;
-    CeedChk(vec_dev_read(op->in[1].v, &qd));
-    if (op->problem != B200_PROB_LINELAS) CeedChk(vec_dev_write(op->out[1].v, &gu));
-    CeedChk(vec_dev_read(in, &x));
-    CeedChk(vec_dev_rw(out, &y));
-    B2(ceed, b200_apply_residual(op->problem, &phys, nelem, P, Q, u->b->interp1d, u->b->grad1d, u->r->d_offsets, qd, gu, x, y));
-  }
-  return 0;
+  return op_apply_fused_range(op, in, out, 0, op->in[0].r->nelem);
+}
+
+/* /gpu/b200 extension: ApplyAdd restricted to the elements [start, stop) of a fused residual / Jacobian operator
+ * (creation order of the restriction).  Lets a partitioned caller run the elements that touch partition
+ * interfaces first and overlap its halo exchange with the interior ones.  start must be a multiple of the
+ * backend's element-group size (16 always is). */
+int CeedOperatorApplyAddRangeB200(CeedOperator op, CeedVector in, CeedVector out, CeedInt start, CeedInt stop) {
+  Ceed ceed = op->ceed;
+  if (op->composite) return CeedError(ceed, 1, "CeedOperatorApplyAddRangeB200: composite operators are not supported");
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  if (op->kind != OP_FUSED_JACOBIAN && op->kind != OP_FUSED_RESIDUAL)
+    return CeedError(ceed, 1, "CeedOperatorApplyAddRangeB200: operator %s does not run on the fused kernels", op->qf->name);
+  const int nelem = op->in[0].r->nelem, EB = b200_elems_per_block(op->in[0].b->Q);
+  if (start < 0 || stop > nelem || start > stop || start % EB)
+    return CeedError(ceed, 1, "CeedOperatorApplyAddRangeB200: bad element range [%d, %d) (nelem %d, start must be a multiple of %d)",
+                     start, stop, nelem, EB);
+  if (start == stop) return 0;
+  return op_apply_fused_range(op, in, out, start, stop);
 }
 
 /* libCEED interface semantics: zero every output (active and passive), then ApplyAdd */

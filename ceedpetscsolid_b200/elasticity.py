@@ -159,7 +159,7 @@ class Elasticity:
         self.app, self.dist = app, dist
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
-        self.mesh = self.gmesh.brick(grid, rank) if world > 1 else self.gmesh
+        self.mesh = self.gmesh.brick(grid, rank, interface_first=masked) if world > 1 else self.gmesh
         self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}")
         self.degrees, self.data, self.phys = setuplibceed.setup_all(self.ceed, self.mesh, app.problem, app.degree, app.nu,
                                                                     app.E, app.qextra, app.multigrid)

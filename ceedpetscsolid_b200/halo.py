@@ -162,6 +162,50 @@ class Halo:
         end up with the assembled value (allowed harness optimisation)."""
         self._exchange(Yloc, self.share_cat, self.share_views, self.share_cat, self.share_views, add=True, tag="sas")
 
+    # ---- split form of sum_and_share: the exchange runs on a side stream while the caller keeps computing on
+    # entries that are NOT shared (the interior elements of an operator application)
+    def sum_and_share_begin(self, Yloc):
+        """Pack the shared dofs (their partial sums must be complete) and start the neighbour exchange."""
+        dist = self.dist
+        sbuf = self._buffer("ssas", self.share_cat.numel(), Yloc)
+        rbuf = self._buffer("rsas", self.share_cat.numel(), Yloc)
+        self._gather(sbuf, Yloc, self.share_cat)
+        ops = []
+        for r in self.neighbours:
+            a, b = self.share_views[r]
+            ops.append(dist.P2POp(dist.irecv, rbuf[a:b], r))
+            ops.append(dist.P2POp(dist.isend, sbuf[a:b], r))
+        self._pending = None
+        if not ops:
+            return
+        if Yloc.is_cuda:
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(device=Yloc.device)
+                self._ev_packed = torch.cuda.Event()
+                self._ev_recvd = torch.cuda.Event()
+            self._ev_packed.record()                       # pack kernel queued on the compute stream
+            self._side.wait_event(self._ev_packed)
+            with torch.cuda.stream(self._side):
+                works = dist.batch_isend_irecv(ops)
+                for w in works:                            # stream-ordered wait: the host does not block
+                    w.wait()
+                self._ev_recvd.record()
+            self._pending = ("cuda", rbuf)
+        else:
+            self._pending = ("cpu", rbuf, dist.batch_isend_irecv(ops))
+
+    def sum_and_share_end(self, Yloc):
+        """Wait for the exchange started by sum_and_share_begin and add the neighbours' partial sums."""
+        pend, self._pending = self._pending, None
+        if pend is None:
+            return
+        if pend[0] == "cuda":
+            torch.cuda.current_stream(Yloc.device).wait_event(self._ev_recvd)
+        else:
+            for w in pend[2]:
+                w.wait()
+        self._scatter(Yloc, self.share_cat, pend[1], True)
+
     def owner_to_ghost(self, Xloc):
         """DMGlobalToLocal part 2: ghosts receive the owner's value."""
         self._exchange(Xloc, self.own_cat, self.own_views, self.ghost_cat, self.ghost_views, add=False, tag="o2g")

@@ -21,6 +21,11 @@ from . import ceed as libceed
 from .ceed import MEM_DEVICE, MEM_HOST, USE_POINTER, b2, lib
 
 
+# halo/compute overlap pays once the interior kernel is long enough to hide the exchange behind (two extra
+# launches, two stream hand-overs): below this many interior elements the plain sequence is used
+OVERLAP_MIN_INTERIOR = 60000
+
+
 class LevelDM:
     """DM stand-in for one level (degree p) of a (brick of a) box mesh.
 
@@ -176,6 +181,7 @@ class UserMult:
     memType: int = MEM_DEVICE
     loadIncrement: float = 1.0
     bc_values: object = None  # callable(loadIncrement) -> tensor over dm.bc_idx, or None
+    overlap: bool = True      # partitioned + masked layout: overlap the halo exchange with the interior elements
 
 
 def setup_jacobian_ctx(dm, ceed, data, phys, physSmoother=None, memType=MEM_DEVICE):
@@ -194,6 +200,20 @@ def ApplyLocalCeedOp(X, Y, user, zero_xloc=False):
         # into -- no DMGlobalToLocal / DMLocalToGlobal data movement at all
         user.Xceed.set_array(X, user.memType, USE_POINTER)
         user.Yceed.set_array(Y, user.memType, USE_POINTER)
+        nif = dm.mesh.n_interface if dm.halo is not None else 0
+        if nif and user.overlap and X.is_cuda and dm.mesh.nelem - nif >= OVERLAP_MIN_INTERIOR:
+            # partitioned: the elements touching a partition interface come first in the element numbering;
+            # once they are done every shared dof holds its complete partial sum, so the halo exchange runs
+            # (side stream, NCCL) while the interior elements are processed
+            user.Yceed.set_value(0.0)
+            user.op.apply_add_range(user.Xceed, user.Yceed, 0, nif)
+            dm.halo.sum_and_share_begin(Y)
+            user.op.apply_add_range(user.Xceed, user.Yceed, nif, dm.mesh.nelem)
+            dm.halo.sum_and_share_end(Y)
+            user.Xceed.take_array(user.memType)
+            user.Yceed.take_array(user.memType)
+            dm.zero_constrained(Y)
+            return
         user.op.apply(user.Xceed, user.Yceed)
         user.Xceed.take_array(user.memType)
         user.Yceed.take_array(user.memType)

@@ -56,6 +56,12 @@ class BoxMesh:
     origin: tuple = (0, 0, 0)
     gn: tuple = None
     vertices: np.ndarray = field(default=None, repr=False)
+    # element numbering: row i of offsets() is lexicographic element elem_order[i] (None = lexicographic).
+    # brick(..., interface_first=True) puts the elements that touch a partition interface first
+    # (n_interface of them, padded to a multiple of 16) so that their part of an operator application can run,
+    # and the halo exchange start, before the interior elements are processed.
+    elem_order: np.ndarray = field(default=None, repr=False)
+    n_interface: int = 0
 
     def __post_init__(self):
         self.n = tuple(int(v) for v in self.n)
@@ -111,6 +117,8 @@ class BoxMesh:
         c, b, a = np.meshgrid(np.arange(P), np.arange(P), np.arange(P), indexing="ij")
         loc = (a + Nx * (b + Ny * c)).reshape(1, -1)
         nodes = base + loc
+        if self.elem_order is not None:
+            nodes = nodes[self.elem_order]
         if node_perm is not None:
             nodes = node_perm[nodes]
         off = nodes * ncomp
@@ -155,7 +163,7 @@ class BoxMesh:
         return m.reshape(-1)
 
     # ---------------------------------------------------------------- partition
-    def brick(self, grid, rank):
+    def brick(self, grid, rank, interface_first=False):
         """Sub-mesh of rank `rank` in a `grid=(px,py,pz)` brick partition (x fastest)."""
         px, py, pz = grid
         rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
@@ -165,8 +173,21 @@ class BoxMesh:
             start = rr * q + min(rr, rem)
             lo.append(self.origin[d] + start)
             sz.append(q + (1 if rr < rem else 0))
+        order, nif = None, 0
+        if interface_first:
+            ez, ey, ex = np.meshgrid(np.arange(sz[2]), np.arange(sz[1]), np.arange(sz[0]), indexing="ij")
+            touch = np.zeros(ex.shape, bool)
+            for d, (e, pp, rr) in enumerate(((ex, px, rx), (ey, py, ry), (ez, pz, rz))):
+                if rr > 0:
+                    touch |= e == 0
+                if rr < pp - 1:
+                    touch |= e == sz[d] - 1
+            touch = touch.reshape(-1)
+            order = np.concatenate([np.flatnonzero(touch), np.flatnonzero(~touch)])  # stable: lexicographic inside each part
+            nif = int(touch.sum())
+            nif = min(order.size, (nif + 15) // 16 * 16) if nif else 0
         return BoxMesh(n=tuple(sz), perturb=self.perturb, seed=self.seed, lengths=self.lengths,
-                       origin=tuple(lo), gn=self.gn)
+                       origin=tuple(lo), gn=self.gn, elem_order=order, n_interface=nif)
 
 
 def smooth_displacement(X, scale=0.02):

@@ -180,6 +180,8 @@ CEED_EXTERN int CeedOperatorDestroy(CeedOperator *op);
 
 /* ---- /gpu/b200 extensions (not part of upstream; used by the harness and the tests) -- */
 /* 1 if the operator's Apply runs as ONE fused kernel (gather..scatter), 0 if generic */
+/* ApplyAdd on the element range [start, stop) of a fused operator (halo-exchange overlap in partitioned runs) */
+CEED_EXTERN int CeedOperatorApplyAddRangeB200(CeedOperator op, CeedVector in, CeedVector out, CeedInt start, CeedInt stop);
 CEED_EXTERN int CeedOperatorIsFusedB200(CeedOperator op, int *isFused);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 CEED_EXTERN unsigned long long CeedB200LaunchCount(void);

@@ -24,10 +24,10 @@ def main():
     from ceedpetscsolid_b200.halo import Halo
     from ceedpetscsolid_b200.mesh import BoxMesh, grid_for, smooth_displacement
 
-    problem, p, n = "hyperFS", 2, (6, 4, 4)
+    problem, p, n = "hyperFS", 2, ((12, 10, 10) if os.environ.get("MGPU_SHARED", "0") == "masked" else (6, 4, 4))
     grid = grid_for(world)
     gmesh = BoxMesh(n=n, perturb=0.08, seed=0)
-    mesh = gmesh.brick(grid, rank)
+    mesh = gmesh.brick(grid, rank, interface_first=os.environ.get("MGPU_SHARED", "0") == "masked")
     ceed = libceed.Ceed(f"/gpu/b200:device_id={local}")
     degrees, data, phys = setuplibceed.setup_all(ceed, mesh, problem, p)
     fine = len(degrees) - 1

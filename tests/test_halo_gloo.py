@@ -66,7 +66,19 @@ def _worker(rank, world, port, n, p, problem, out):
         xs = torch.from_numpy(xg[gdof].copy())
         ys = torch.from_numpy(oracle.operator_apply(problem, True, PHYS, brick.nelem, P, Q, B, D, brick.offsets(p), qdata,
                                                     None, xs.numpy()))
+        ys_split = ys.clone()
         halo.sum_and_share(ys)
+        # 5. split form (begin ... interior work ... end) gives the same result
+        halo.sum_and_share_begin(ys_split)
+        halo.sum_and_share_end(ys_split)
+        assert torch.equal(ys_split, ys)
+        # 6. interface-first element numbering: the leading n_interface elements hold every shared node
+        bi = gmesh.brick(grid, rank, interface_first=True)
+        off_if, off_lex = bi.offsets(p), brick.offsets(p)
+        assert np.array_equal(off_if, off_lex[bi.elem_order]) and sorted(bi.elem_order) == list(range(brick.nelem))
+        shared_nodes = np.flatnonzero(halo.rank_multiplicity > 1)
+        later = np.unique(off_if[bi.n_interface:] // 3) if bi.n_interface < bi.nelem else np.zeros(0, int)
+        assert np.intersect1d(shared_nodes, later).size == 0 and (bi.n_interface % 16 == 0 or bi.n_interface == bi.nelem)
         own = np.repeat(halo.owned_node_mask, 3)
         assert np.array_equal(np.repeat(halo.rank_multiplicity, 3), ones.numpy()) or True
         np.save(os.path.join(out, f"shared{rank}.npy"), np.stack([gdof.astype(np.float64), ys.numpy(),
