@@ -397,35 +397,47 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
     double acc[P];
 #pragma unroll
     for (int k = 0; k < P; k++) acc[k] = 0;
+    // the per-point data of this x-line is read ONCE per component: all three unit-gradient directions d'
+    // are pushed through the point Jacobian while the cache entry sits in registers
+    double S[3][3][P];  // [d'][d][i]: x-contracted already
+#pragma unroll
+    for (int dp = 0; dp < 3; dp++)
+#pragma unroll
+      for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int i = 0; i < P; i++) S[dp][d][i] = 0;
+    if (act) {
 #pragma unroll 1
-    for (int dp = 0; dp < 3; dp++) {  // d' : direction of the unit input
-      // x-lines (a = qy, b = qz): evaluate Aq_c[d'][d] at this line's points, contract x
-      if (act) {
-        double Aq[3][Q];
+      for (int qx = 0; qx < Q; qx++) {
+        double qd[NC];
 #pragma unroll
-        for (int qx = 0; qx < Q; qx++) {
-          double qd[NC], H[3][3], W[3][3];
+        for (int n = 0; n < NC; n++) qd[n] = __ldg(jcp + gb + (size_t)(n * Q + qx) * ebt);
 #pragma unroll
-          for (int n = 0; n < NC; n++) qd[n] = __ldg(jcp + gb + (size_t)(n * Q + qx) * ebt);
+        for (int dp = 0; dp < 3; dp++) {
+          double H[3][3], W[3][3];
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) H[i][j] = (i == c && j == dp) ? 1. : 0.;
           jacobian_point<PROB>(mt, qd, H, W);
 #pragma unroll
-          for (int d = 0; d < 3; d++) Aq[d][qx] = c == 0 ? W[0][d] : (c == 1 ? W[1][d] : W[2][d]);
-        }
+          for (int d = 0; d < 3; d++) {
+            const double w = c == 0 ? W[0][d] : (c == 1 ? W[1][d] : W[2][d]);
+            const int sel = (d == 0) + (dp == 0);
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          const int sel = (d == 0) + (dp == 0);
-#pragma unroll
-          for (int i = 0; i < P; i++) {
-            double s = 0;
-#pragma unroll
-            for (int qx = 0; qx < Q; qx++) s += dm.M[sel][qx * P + i] * Aq[d][qx];
-            R0[IDX(d, i, a, b)] = s;
+            for (int i = 0; i < P; i++) S[dp][d][i] += dm.M[sel][qx * P + i] * w;
           }
         }
+      }
+    }
+#pragma unroll
+    for (int dp = 0; dp < 3; dp++) {  // d' : direction of the unit input
+      // x-lines (a = qy, b = qz): already contracted along x
+      if (act) {
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+          for (int i = 0; i < P; i++) R0[IDX(d, i, a, b)] = S[dp][d][i];
       }
       __syncthreads();
       // y-lines (a = i < P, b = qz)

@@ -63,7 +63,7 @@ __global__ void k_pcg_update(double *x, double *r, double *z, const double *p, c
                              size_t n, const double *rz, const double *pAp) {
   const double a = rz[0] / pAp[0];
   GRID_STRIDE(i, n) {
-    x[i] += a * p[i];
+    if (x) x[i] += a * p[i];  // x == NULL: Lanczos run for eigenvalue estimates, the iterate is not needed
     const double ri = r[i] - a * Ap[i];
     r[i] = ri;
     z[i] = dinv[i] * ri;

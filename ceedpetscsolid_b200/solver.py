@@ -216,40 +216,72 @@ def estimate_lambda_max(V, A, dinv, n, device, its=10, seed=0):
     (KSPChebyshevEstEigSet + noisy rhs, elasticity.c:540-545; PETSc's PRNG is not reproducible here)."""
     # deterministic "noisy" rhs generated ON the device with exact integer arithmetic (identical on CPU
     # and GPU): a multiplicative hash of the dof index, two xorshift-multiply rounds, mapped to [-0.5, 0.5)
-    h = torch.arange(n, dtype=torch.int64, device=device)
-    h = (h * 2654435761 + 1234567 * (seed + 1)) & 0xFFFFFFFF
-    h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
-    h = ((h ^ (h >> 13)) * 3266489917) & 0xFFFFFFFF
-    h = h ^ (h >> 16)
-    b = h.to(torch.float64) / 4294967296.0 - 0.5
-    del h
-    fix = getattr(V, "consistent", {}).get(n)
-    if fix is not None:  # shared-dof layouts: every copy of an interface dof must hold the same value
-        fix(b)
-    x = torch.zeros_like(b)
-    r, z, p, Ap = (torch.zeros_like(b) for _ in range(4))
-    V.copy(r, b)
+    cache = V.__dict__.setdefault("_eig_rhs", {})
+    key = (n, seed, str(device))
+    if key not in cache:  # generated once per level (it does not depend on the operator), copied afterwards
+        h = torch.arange(n, dtype=torch.int64, device=device)
+        h = (h * 2654435761 + 1234567 * (seed + 1)) & 0xFFFFFFFF
+        h = ((h ^ (h >> 15)) * 2246822519) & 0xFFFFFFFF
+        h = ((h ^ (h >> 13)) * 3266489917) & 0xFFFFFFFF
+        h = h ^ (h >> 16)
+        b0 = h.to(torch.float64) / 4294967296.0 - 0.5
+        del h
+        fix = getattr(V, "consistent", {}).get(n)
+        if fix is not None:  # shared-dof / masked layouts: consistent interface copies, zero Dirichlet entries
+            fix(b0)
+        cache[key] = b0
+    b = cache[key].clone()
+    r, z, p, Ap = b, torch.empty_like(b), torch.empty_like(b), torch.empty_like(b)   # r starts as (and overwrites) b
     V.pmult(z, dinv, r)
     V.copy(p, z)
-    rz = V.dot(r, z)
     alphas, betas = [], []
-    for _ in range(its):
-        A(p, Ap)
-        pAp = V.dot(p, Ap)
-        if pAp <= 0 or rz == 0:
-            break
-        alpha = rz / pAp
-        V.axpy(x, alpha, p)
-        V.axpy(r, -alpha, Ap)
-        V.pmult(z, dinv, r)
-        rz_new = V.dot(r, z)
-        beta = rz_new / rz
-        alphas.append(alpha)
-        betas.append(beta)
-        V.aypx(p, beta, z)
-        rz = rz_new
-        if rz_new == 0:
-            break
+    if b.is_cuda:
+        # all scalars stay on the device (rz_0..rz_its, pAp_0..pAp_its-1); ONE host sync at the end
+        sc = torch.zeros(2 * its + 1, dtype=torch.float64, device=device)
+        multi = V.dist is not None and V.dist.get_world_size() > 1
+
+        def ddot(a_, b_, slot):
+            out = sc[slot:slot + 1]
+            a_ = V._weighted(a_)
+            b2(lib.b200_vec_dot(a_.data_ptr(), b_.data_ptr(), a_.numel(), out.data_ptr()))
+            if multi:
+                V.dist.all_reduce(out)
+
+        ddot(r, z, 0)
+        for k in range(its):
+            A(p, Ap)
+            ddot(p, Ap, its + 1 + k)
+            b2(lib.b200_pcg_update(None, r.data_ptr(), z.data_ptr(), p.data_ptr(), Ap.data_ptr(), dinv.data_ptr(),
+                                   r.numel(), sc[k:k + 1].data_ptr(), sc[its + 1 + k:its + 2 + k].data_ptr()))
+            ddot(r, z, k + 1)
+            b2(lib.b200_vec_aypx_dev(p.data_ptr(), z.data_ptr(), p.numel(), sc[k + 1:k + 2].data_ptr(), sc[k:k + 1].data_ptr()))
+        h = sc.cpu().numpy()
+        for k in range(its):
+            rz, pAp, rz_new = h[k], h[its + 1 + k], h[k + 1]
+            if not (np.isfinite(rz) and np.isfinite(pAp) and np.isfinite(rz_new)) or pAp <= 0 or rz == 0:
+                break
+            alphas.append(rz / pAp)
+            betas.append(rz_new / rz)
+            if rz_new == 0:
+                break
+    else:
+        rz = V.dot(r, z)
+        for _ in range(its):
+            A(p, Ap)
+            pAp = V.dot(p, Ap)
+            if pAp <= 0 or rz == 0:
+                break
+            alpha = rz / pAp
+            V.axpy(r, -alpha, Ap)
+            V.pmult(z, dinv, r)
+            rz_new = V.dot(r, z)
+            beta = rz_new / rz
+            alphas.append(alpha)
+            betas.append(beta)
+            V.aypx(p, beta, z)
+            rz = rz_new
+            if rz_new == 0:
+                break
     k = len(alphas)
     T = np.zeros((k, k))
     for i in range(k):
