@@ -153,13 +153,13 @@ class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
     def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg",
-                 assemble="coo", masked=True):
+                 assemble="coo", masked=True, overlap=False):
         """masked: constrained dofs are masked in L-vector-shaped global vectors (no G2L/L2G copies, see LevelDM);
         False: compressed PETSc-style global vectors."""
         self.app, self.dist = app, dist
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
-        self.mesh = self.gmesh.brick(grid, rank, interface_first=masked) if world > 1 else self.gmesh
+        self.mesh = self.gmesh.brick(grid, rank, interface_first=masked and overlap) if world > 1 else self.gmesh
         self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}")
         self.degrees, self.data, self.phys = setuplibceed.setup_all(self.ceed, self.mesh, app.problem, app.degree, app.nu,
                                                                     app.E, app.qextra, app.multigrid)

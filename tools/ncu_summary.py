@@ -49,10 +49,10 @@ cold-cache and serialised; the SHARE is what matters.
 
 {chr(10).join(lt)}
 
-Per timed step the launches are: `k_gather_or_zero` (VecZeroEntries(Xloc) + DMGlobalToLocal in one pass), one memset
-(CeedOperatorApply zeroing its output), `k_fused_apply<5,5,2,1>` (the whole CeedOperatorApply), `k_gather`
-(DMLocalToGlobal).  The fused kernel is {fused[1] / fused[0]:.0f} us of the ~{fused[1] / fused[0] + per_step.get('k_gather_or_zero', 0) + per_step.get('k_gather', 0) + 10:.0f} us step here
-(~70 %), matching bench.py at 64^3 (1.25 ms of 1.77 ms).  `k_fused_apply<5,5,2,0>` is the residual evaluation that fills
+Per timed step (masked DM layout, the bench default) the launches are: one fill kernel (CeedOperatorApply zeroing its
+output), `k_fused_apply<5,5,2,1>` (the whole CeedOperatorApply, reading X and accumulating into Y directly) and
+`k_mask_zero` (Dirichlet rows of Y).  The fused kernel is {fused[1] / fused[0]:.0f} us of the ~{fused[1] / fused[0] + per_step.get('k_mask_zero', 0) + 9:.0f} us step here
+(~{100 * (fused[1] / fused[0]) / (fused[1] / fused[0] + per_step.get('k_mask_zero', 0) + 9):.0f} %), matching bench.py at 64^3 (1.238 ms of 1.317 ms = 94 %).  `k_fused_apply<5,5,2,0>` is the residual evaluation that fills
 gradu once; `k_restrict_strided`, `k_basis_apply`, `k_qfunction` are the one-off SetupGeo operator on the generic path;
 `k_jcache_build<2>` builds the Jacobian cache once.
 """)
