@@ -24,7 +24,7 @@ template <int Q> struct AsmMats {
 // q-blocked slab.  The thread walks the Q^3 points once, pushes the column's unit gradient through the point
 // Jacobian and accumulates its 24 row entries in registers.
 // FP64 work: Q^3 x 24 x (~135 point Jacobian + 72 test-side + 12 shape) ~ 0.66 MFLOP per element at Q = 5;
-// bytes: NC x Q^3 x 8 read (17 kB) + 4.6 kB written per element  ->  compute-bound (AI ~ 30 flop/B).
+// bytes: NC x Q^3 x 8 read (16 kB) + 4.6 kB written per element  ->  compute-bound (AI ~ 30 flop/B).
 template <int Q, int PROB>
 __global__ void __launch_bounds__(24 * elems_per_block(Q))
 k_assemble_p1(const __grid_constant__ AsmMats<Q> am, const __grid_constant__ Material mt, int nelem,

@@ -750,7 +750,7 @@ extern "C" int b200_fused_supported(int P, int Q) {
 }
 
 extern "C" int b200_jcache_ncomp(int problem) {
-  return problem == B200_PROB_LINELAS ? 10 : problem == B200_PROB_HYPERSS ? 11 : problem == B200_PROB_HYPERFS ? 17 : -1;
+  return problem == B200_PROB_LINELAS ? 9 : problem == B200_PROB_HYPERSS ? 10 : problem == B200_PROB_HYPERFS ? 16 : -1;
 }
 
 extern "C" int b200_apply_residual(int problem, const b200_physics *phys, int nelem, int P, int Q,

@@ -223,11 +223,13 @@ B200_DI void hyperfs_df_point_faithful(const Material &mt, double w, const doubl
 }
 
 // ------------------------------------------------------------------ Jacobian cache
-// Per quadrature point, the Jacobian action in its cheapest exact algebraic form.
+// Per quadrature point, the Jacobian action in its cheapest exact algebraic form.  Every Jacobian here has the
+// shape  W = w L(H A) A^T  with L linear, so the weight is folded into the geometry: A' = sqrt(w) A gives
+// W = L(H A') A'^T and one double less to stream per point (w = weight x det J > 0).
 //
-//   linElas  (10): w, A                      W = A (w sigma(H A))^T-form, as the reference
-//   hyperSS  (11): w, A, s = 1/(1+tr gradu)  dsigma = lambda s tr(g) I + mu (g + g^T)
-//   hyperFS  (17): w, K = A F^-1, b = F F^T (Voigt), lnJ
+//   linElas  ( 9): A'                         sigma(H A') A'^T, as the reference
+//   hyperSS  (10): A', s = 1/(1+tr gradu)     dsigma = lambda s tr(g) I + mu (g + g^T)
+//   hyperFS  (16): K' = sqrt(w) A F^-1, b = F F^T (Voigt), lnJ
 //       With gt = H K (spatial gradient of the increment) the reference's
 //       dP = grad(du) S + F dS, S = mu I + (lambda lnJ - mu) C^-1, collapses to
 //         W = w [ mu gt b + lambda tr(gt) I + (mu - lambda lnJ) gt^T ] K^T
@@ -235,20 +237,21 @@ B200_DI void hyperfs_df_point_faithful(const Material &mt, double w, const doubl
 //       Material constants are NOT baked in, so GetDiag_Ceed's smoother-context swap
 //       (matops.c:215-217) keeps working.
 template <int PROB> struct JCache;
-template <> struct JCache<B200_PROB_LINELAS> { static constexpr int N = 10; };
-template <> struct JCache<B200_PROB_HYPERSS> { static constexpr int N = 11; };
-template <> struct JCache<B200_PROB_HYPERFS> { static constexpr int N = 17; };
+template <> struct JCache<B200_PROB_LINELAS> { static constexpr int N = 9; };
+template <> struct JCache<B200_PROB_HYPERSS> { static constexpr int N = 10; };
+template <> struct JCache<B200_PROB_HYPERFS> { static constexpr int N = 16; };
 
 // qd[10] = qdata, gu[9] = gradu [c][k]  ->  jc[N]
 template <int PROB>
 B200_DI void jcache_point(const double *qd, const double *gu, double *jc) {
+  const double sw = sqrt(qd[0]);
   if (PROB == B200_PROB_LINELAS) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) jc[i] = qd[i];
+    for (int i = 0; i < 9; i++) jc[i] = sw * qd[1 + i];
   } else if (PROB == B200_PROB_HYPERSS) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) jc[i] = qd[i];
-    jc[10] = 1. / (1. + (gu[0] + gu[4] + gu[8]));
+    for (int i = 0; i < 9; i++) jc[i] = sw * qd[1 + i];
+    jc[9] = 1. / (1. + (gu[0] + gu[4] + gu[8]));
   } else {
     double g[3][3], F[3][3], Fi[3][3], e[6];
 #pragma unroll
@@ -261,7 +264,7 @@ B200_DI void jcache_point(const double *qd, const double *gu, double *jc) {
     const double c00 = F[1][1] * F[2][2] - F[1][2] * F[2][1];
     const double c01 = F[1][2] * F[2][0] - F[1][0] * F[2][2];
     const double c02 = F[1][0] * F[2][1] - F[1][1] * F[2][0];
-    const double rdet = 1. / (F[0][0] * c00 + F[0][1] * c01 + F[0][2] * c02);
+    const double rdet = sw / (F[0][0] * c00 + F[0][1] * c01 + F[0][2] * c02);  // sqrt(w) folded into F^-1
     Fi[0][0] = c00 * rdet;
     Fi[1][0] = c01 * rdet;
     Fi[2][0] = c02 * rdet;
@@ -271,17 +274,16 @@ B200_DI void jcache_point(const double *qd, const double *gu, double *jc) {
     Fi[0][2] = (F[0][1] * F[1][2] - F[0][2] * F[1][1]) * rdet;
     Fi[1][2] = (F[0][2] * F[1][0] - F[0][0] * F[1][2]) * rdet;
     Fi[2][2] = (F[0][0] * F[1][1] - F[0][1] * F[1][0]) * rdet;
-    jc[0] = qd[0];
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
       for (int j = 0; j < 3; j++)
-        jc[1 + 3 * k + j] = qd[1 + 3 * k] * Fi[0][j] + qd[2 + 3 * k] * Fi[1][j] + qd[3 + 3 * k] * Fi[2][j];
+        jc[3 * k + j] = qd[1 + 3 * k] * Fi[0][j] + qd[2 + 3 * k] * Fi[1][j] + qd[3 + 3 * k] * Fi[2][j];
     const int vj[6] = {0, 1, 2, 1, 0, 0}, vk[6] = {0, 1, 2, 2, 2, 1};
 #pragma unroll
     for (int m = 0; m < 6; m++)
-      jc[10 + m] = F[vj[m]][0] * F[vk[m]][0] + F[vj[m]][1] * F[vk[m]][1] + F[vj[m]][2] * F[vk[m]][2];
-    jc[16] = log1p_series_shifted(green_lagrange2(g, e)) / 2.;
+      jc[9 + m] = F[vj[m]][0] * F[vk[m]][0] + F[vj[m]][1] * F[vk[m]][1] + F[vj[m]][2] * F[vk[m]][2];
+    jc[15] = log1p_series_shifted(green_lagrange2(g, e)) / 2.;
   }
 }
 
@@ -293,27 +295,26 @@ B200_DI void jacobian_point(const Material &mt, const double *jc, const double (
 #pragma unroll
   for (int m = 0; m < 3; m++)
 #pragma unroll
-    for (int k = 0; k < 3; k++) A[m][k] = jc[1 + 3 * m + k];
-  const double w = jc[0];
+    for (int k = 0; k < 3; k++) A[m][k] = jc[3 * m + k];
   if (PROB == B200_PROB_LINELAS) {
-    linelas_point(mt, w, A, H, W);
+    linelas_point(mt, 1., A, H, W);
   } else if (PROB == B200_PROB_HYPERSS) {
-    hyperss_df_point(mt, w, A, jc[10], H, W);
+    hyperss_df_point(mt, 1., A, jc[9], H, W);
   } else {
-    // A holds K here
+    // A holds K' here
     double gt[3][3], Z[3][3], bm[3][3];
-    const double bv[6] = {jc[10], jc[11], jc[12], jc[13], jc[14], jc[15]};
+    const double bv[6] = {jc[9], jc[10], jc[11], jc[12], jc[13], jc[14]};
     voigt_sym(bv, bm);
-    phys_grad(A, H, gt);  // gt[c][j] = sum_m H[c][m] K[m][j]
-    const double cw = mt.mu * w, bw = (mt.mu - mt.lambda * jc[16]) * w;
-    const double aw = (mt.lambda * w) * (gt[0][0] + gt[1][1] + gt[2][2]);
+    phys_grad(A, H, gt);  // gt[c][j] = sum_m H[c][m] K'[m][j]
+    const double cw = mt.mu, bw = mt.mu - mt.lambda * jc[15];
+    const double aw = mt.lambda * (gt[0][0] + gt[1][1] + gt[2][2]);
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
       for (int j = 0; j < 3; j++)
         Z[c][j] = cw * (gt[c][0] * bm[0][j] + gt[c][1] * bm[1][j] + gt[c][2] * bm[2][j]) + bw * gt[j][c] +
                   (c == j ? aw : 0.);
-    pull_back(A, Z, W);  // W[c][k] = sum_m K[k][m] Z[c][m]
+    pull_back(A, Z, W);  // W[c][k] = sum_m K'[k][m] Z[c][m]
   }
 }
 
