@@ -347,62 +347,79 @@ class ChebyshevJacobi:
 
 
 class ColoredCoarseMatrix:
-    """FormJacobian (src/misc.c:151-183): the coarse (p = 1) Jacobian assembled from its action on
-    coloured unit vectors -- exact because the action is linear.  Assembled on the LOCAL vector
-    space of the rank (27 node colours x 3 components = 81 operator applies, one ELL slot each);
-    the global action is P^T A_loc P with the same halo exchange as the matrix-free operator."""
+    """FormJacobian (src/misc.c:151-183): the coarse (p = 1) Jacobian, assembled on the LOCAL vector space of the
+    rank and stored as a 27-point block stencil on the node lattice (81 values per row dof); the global action is
+    P^T A_loc P with the same halo exchange as the matrix-free operator.  Two ways to fill it:
+
+    * colouring, as the reference does: the action on 27 node colours x 3 components = 81 coloured unit vectors --
+      exact because the action is linear;
+    * `coo`: element matrices from CeedOperatorLinearAssemble (one pass over the Jacobian cache), summed into the
+      stencil (MatSetValuesCOO stand-in) -- the same entries up to summation order."""
 
     def __init__(self, dm, local_apply, coo=None):
         """coo (optional): object with .elem_nodes (nelem x 8 local node ids, torch, on dm.device) and
-        .values() -> nelem*576 element-matrix entries (CeedOperatorLinearAssemble layout): the matrix is then
-        assembled from one pass over the Jacobian cache instead of the 81 coloured applies -- same entries up to
-        summation order."""
+        .values() -> nelem*576 element-matrix entries in CeedOperatorLinearAssemble layout."""
         self.dm, self.local_apply, self.coo = dm, local_apply, coo
         self.coo_dest = None
-        N = dm.mesh.nodes_per_dim(1)
-        self.N = N
-        n = dm.lsize
-        dev = dm.device
+        self.N = N = dm.mesh.nodes_per_dim(1)
+        n, dev = dm.lsize, dm.device
         k, j, i = np.meshgrid(np.arange(N[2]), np.arange(N[1]), np.arange(N[0]), indexing="ij")
         self.ijk = [a.reshape(-1) for a in (i, j, k)]
-        self.cols = torch.full((81, n), -1, dtype=torch.int32, device=dev)
-        self.vals = torch.zeros((81, n), dtype=torch.float64, device=dev)
-        self.x = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.y = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.seeds = []
+        self.svals = torch.zeros((81, n), dtype=torch.float64, device=dev)  # [(o*3 + a)][row], o = (dx+1)+3(dy+1)+9(dz+1)
+        self.Xloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.Yloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._colouring = None   # built on the first coloured assembly
+        self._nbr = None         # CPU mat-vec: neighbour dof table, built on first use
+
+    # ---- colouring (src/misc.c:151-183)
+    def _setup_colouring(self):
+        N, n, dev = self.N, self.dm.lsize, self.dm.device
         nn = N[0] * N[1] * N[2]
+        i, j, k = self.ijk
+        mask = np.zeros((81, n), dtype=bool)     # slot (colour, a) of a row exists: that colour's neighbour is inside
+        seeds = []
         for color in range(27):
             cc = (color % 3, (color // 3) % 3, color // 9)
-            tgt = []
             ok = np.ones(nn, bool)
             for d in range(3):
                 off = ((cc[d] - self.ijk[d] % 3 + 1) % 3) - 1  # in {-1,0,1}: neighbour of that colour along d
                 t = self.ijk[d] + off
                 ok &= (t >= 0) & (t < N[d])
-                tgt.append(t)
-            colnode = tgt[0] + N[0] * (tgt[1] + N[1] * tgt[2])
-            seed_nodes = np.flatnonzero((self.ijk[0] % 3 == cc[0]) & (self.ijk[1] % 3 == cc[1]) & (self.ijk[2] % 3 == cc[2]))
+            seed_nodes = np.flatnonzero((i % 3 == cc[0]) & (j % 3 == cc[1]) & (k % 3 == cc[2]))
             for a in range(3):
-                s = color * 3 + a
-                col = np.where(ok, colnode * 3 + a, -1).astype(np.int32)
-                self.cols[s] = torch.from_numpy(np.repeat(col, 3)).to(dev)
-                self.seeds.append(torch.from_numpy((seed_nodes * 3 + a).astype(np.int64)).to(dev))
-        self.Xloc = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.Yloc = torch.zeros(n, dtype=torch.float64, device=dev)
-        self._build_stencil_map()
+                mask[color * 3 + a] = np.repeat(ok, 3)
+                seeds.append(torch.from_numpy((seed_nodes * 3 + a).astype(np.int64)).to(dev))
+        # svals[(o*3 + a)][row] = vals[colour(node + d_o)*3 + a][row]; neighbours outside the lattice point at
+        # slots that the mask has zeroed
+        src = np.zeros((81, n), dtype=np.int64)
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    o = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)
+                    color = ((i + dx) % 3) + 3 * ((j + dy) % 3) + 9 * ((k + dz) % 3)
+                    for a in range(3):
+                        src[o * 3 + a] = np.repeat(color * 3 + a, 3)
+        self._colouring = dict(seeds=seeds, mask=torch.from_numpy(mask).to(dev).to(torch.float64),
+                               src=torch.from_numpy(src).to(dev),
+                               vals=torch.zeros((81, n), dtype=torch.float64, device=dev),
+                               x=torch.zeros(n, dtype=torch.float64, device=dev),
+                               y=torch.zeros(n, dtype=torch.float64, device=dev))
 
     def assemble(self):
-        """81 local operator applies (ApplyJacobianCoarse_Ceed without the halo: A_loc itself), then the
-        colour slots are re-indexed by neighbour offset: a 27-point block stencil on the node lattice."""
+        """coo: one pass over the Jacobian cache.  Otherwise 81 local operator applies (ApplyJacobianCoarse_Ceed
+        without the halo: A_loc itself), colour slots re-indexed by neighbour offset."""
         if self.coo is not None:
             return self._assemble_coo()
+        if self._colouring is None:
+            self._setup_colouring()
+        c = self._colouring
         for s in range(81):
-            self.x.zero_()
-            self.x[self.seeds[s]] = 1.0
-            self.local_apply(self.x, self.y)
-            self.vals[s].copy_(self.y)
-        self.vals.mul_((self.cols >= 0).to(torch.float64))
-        torch.gather(self.vals, 0, self.stencil_src, out=self.svals)
+            c["x"].zero_()
+            c["x"][c["seeds"][s]] = 1.0
+            self.local_apply(c["x"], c["y"])
+            c["vals"][s].copy_(c["y"])
+        c["vals"].mul_(c["mask"])
+        torch.gather(c["vals"], 0, c["src"], out=self.svals)
 
     def _assemble_coo(self):
         """MatSetValuesCOO stand-in: element-matrix entries summed into the 27-point block stencil."""
@@ -420,30 +437,23 @@ class ColoredCoarseMatrix:
         self.svals.zero_()
         self.svals.view(-1).index_add_(0, self.coo_dest, self.coo.values())
 
-    def _build_stencil_map(self):
-        """svals[(o*3 + a)][row] = vals[colour(node + d_o)*3 + a][row], o = (dx+1) + 3(dy+1) + 9(dz+1)."""
-        N, n = self.N, self.dm.lsize
-        i, j, k = self.ijk
-        src = np.zeros((81, n), dtype=np.int64)
-        for dz in (-1, 0, 1):
-            for dy in (-1, 0, 1):
-                for dx in (-1, 0, 1):
-                    o = (dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)
-                    color = ((i + dx) % 3) + 3 * ((j + dy) % 3) + 9 * ((k + dz) % 3)  # colour of the neighbour node
-                    for a in range(3):
-                        src[o * 3 + a] = np.repeat(color * 3 + a, 3)
-        # neighbours outside the lattice point at slots whose value is already zero (masked in assemble)
-        self.stencil_src = torch.from_numpy(src).to(self.dm.device)
-        self.svals = torch.zeros((81, n), dtype=torch.float64, device=self.dm.device)
-
     def local_mult(self, xloc, yloc):
         """y_loc = A_loc x_loc (the rank-local, un-assembled matrix)"""
         if xloc.is_cuda:
             b2(lib.b200_stencil27_spmv(self.N[0], self.N[1], self.N[2], self.svals.data_ptr(), xloc.data_ptr(),
                                        yloc.data_ptr()))
-        else:
-            c = self.cols.long().clamp_min(0)
-            yloc.copy_((self.vals * xloc[c] * (self.cols >= 0)).sum(0))
+            return
+        if self._nbr is None:  # [(o*3 + a)][row] -> column dof, or -1 outside the lattice
+            N, (i, j, k) = self.N, self.ijk
+            nbr = np.full((81, self.dm.lsize), -1, dtype=np.int64)
+            for o in range(27):
+                dx, dy, dz = o % 3 - 1, (o // 3) % 3 - 1, o // 9 - 1
+                ok = (i + dx >= 0) & (i + dx < N[0]) & (j + dy >= 0) & (j + dy < N[1]) & (k + dz >= 0) & (k + dz < N[2])
+                col = (i + dx) + N[0] * ((j + dy) + N[1] * (k + dz))
+                for a in range(3):
+                    nbr[o * 3 + a] = np.repeat(np.where(ok, col * 3 + a, -1), 3)
+            self._nbr = torch.from_numpy(nbr)
+        yloc.copy_((self.svals * xloc[self._nbr.clamp_min(0)] * (self._nbr >= 0)).sum(0))
 
     def mult(self, X, Y):
         dm = self.dm

@@ -134,3 +134,51 @@ def test_forcing_operators_match_the_oracle():
         setuplibceed.setup_forcing(c, mesh, data, forcing, phys, (0.3, -1.0, 2.5), fc)
         got = fc.to_numpy()
         assert np.linalg.norm(got - ref) < 1e-12 * np.linalg.norm(ref), forcing
+
+
+def test_coo_to_stencil_map_and_stencil_matvec_on_cpu():
+    """MatSetValuesCOO stand-in (ColoredCoarseMatrix._assemble_coo) against a dense assembly of the same element
+    matrices, and against the coloured assembly of the same operator; CPU tensors, random symmetric element blocks."""
+    from ceedpetscsolid_b200 import matops, solver
+    from ceedpetscsolid_b200.mesh import BoxMesh
+    mesh = BoxMesh(n=(3, 2, 4))
+    dm = matops.LevelDM(mesh, 1, bc_faces=[(2, 0)], device="cpu")
+    off = mesh.offsets(1)                                  # (E, 8) component-0 dof of each element node
+    E = off.shape[0]
+    rng = np.random.default_rng(2)
+    Ke = rng.standard_normal((E, 24, 24))
+    Ke = Ke + Ke.transpose(0, 2, 1)
+    eld = (off[:, :, None] + np.arange(3)[None, None, :]).reshape(E, 24)   # element dof = node*3 + comp
+    n = dm.lsize
+    A = np.zeros((n, n))
+    for e in range(E):
+        A[np.ix_(eld[e], eld[e])] += Ke[e]
+
+    class Coo:
+        elem_nodes = torch.from_numpy(off // 3)
+
+        @staticmethod
+        def values():  # CeedOperatorLinearAssemble layout: [e][col][row]
+            return torch.from_numpy(np.ascontiguousarray(Ke.transpose(0, 2, 1)).reshape(-1))
+
+    def local_apply(x, y):
+        y.copy_(torch.from_numpy(A @ x.numpy()))
+
+    m_coo = solver.ColoredCoarseMatrix(dm, local_apply, coo=Coo())
+    m_col = solver.ColoredCoarseMatrix(dm, local_apply)
+    m_coo.assemble()
+    m_col.assemble()
+    assert torch.allclose(m_coo.svals, m_col.svals, rtol=0, atol=1e-12)
+    x = torch.from_numpy(rng.standard_normal(n))
+    y = torch.zeros(n, dtype=torch.float64)
+    m_coo.local_mult(x, y)
+    assert np.allclose(y.numpy(), A @ x.numpy(), rtol=0, atol=1e-11)
+    # global action and diagonal with the Dirichlet face eliminated
+    X = torch.from_numpy(rng.standard_normal(dm.nglobal))
+    Y = torch.zeros(dm.nglobal, dtype=torch.float64)
+    m_coo.mult(X, Y)
+    free = dm._fo_host
+    assert np.allclose(Y.numpy(), A[np.ix_(free, free)] @ X.numpy(), rtol=0, atol=1e-11)
+    D = torch.zeros(dm.nglobal, dtype=torch.float64)
+    m_coo.diagonal(D)
+    assert np.allclose(D.numpy(), np.diag(A)[free], rtol=0, atol=1e-12)
