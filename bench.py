@@ -129,7 +129,8 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                  clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1 * lengths[2], 0, 0, 1, 0]})
     gmesh = BoxMesh(n=n, perturb=app.perturb, seed=0, lengths=lengths)
     el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank, gmesh=gmesh,
-                    coarse_rtol=args.coarse_rtol, coarse=args.coarse, assemble=args.assemble, masked=args.dm == "masked")
+                    coarse_rtol=args.coarse_rtol, coarse=args.coarse, assemble=args.assemble, masked=args.dm == "masked",
+                    halo=args.halo)
     el.pc.coarse_maxit = args.coarse_maxit
     libceed.launch_count_reset()
     sampler = ClockSampler(local_rank)
@@ -180,6 +181,9 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="N > 1: interface elements first, halo exchange on a side stream overlapped with the interior "
                          "elements (measured slower than the plain sequence at 8 GPUs without high-priority NCCL streams)")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: interface exchange through NCCL send/recv, or stored straight into the neighbours' "
+                         "windows over NVLink peer memory (csrc/b200_halo.cu)")
     ap.add_argument("--assemble", default="coo", choices=["coo", "color"], help="p=1 matrix: CeedOperatorLinearAssemble element matrices, or 81 coloured applies (misc.c:151-183)")
     ap.add_argument("--coarse", default="hmg", choices=["hmg", "pcg"], help="coarse solve on the assembled p=1 level: h-multigrid (GAMG stand-in) or Jacobi-PCG")
     args = ap.parse_args()
@@ -244,6 +248,9 @@ def main():
     if world > 1:
         from ceedpetscsolid_b200.halo import Halo
         halo = Halo(gmesh, grid, rank, p, dist)
+        if args.halo == "p2p":
+            halo.enable_p2p()
+            config["halo"] = "NVLink peer-memory windows (CUDA IPC), one sum-and-share per MatMult, no NCCL on the data path"
     # N > 1: shared-dof global vectors -> one symmetric sum-and-share halo exchange per MatMult
     masked = args.dm == "masked"
     config["dm"] = ("masked constrained dofs: Krylov vectors have the L-vector layout, no G2L/L2G copies" if masked
@@ -282,6 +289,8 @@ def main():
     barrier()
     launches = libceed.launch_count()
     clocks = sampler.result()
+    if halo is not None:
+        halo.check_p2p()   # a timed-out peer-memory exchange invalidates the run: fail loudly
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")

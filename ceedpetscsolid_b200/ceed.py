@@ -140,6 +140,11 @@ _proto("b200_vec_aypx_dev", _vp, _vp, _sz, _vp, _vp)
 _proto("b200_pcg_update", _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp)
 _proto("b200_stencil27_spmv", _i, _i, _i, _vp, _vp, _vp)
 _proto("b200_stencil27_galerkin", _i, _i, _i, _vp, _vp)
+_proto("b200_ipc_get_handle", _vp, _vp)
+_proto("b200_ipc_open", _vp, _pvp)
+_proto("b200_ipc_close", _vp)
+_proto("b200_halo_push_signal", _i, _vp, _vp, _vp, _vp, _vp, C.c_longlong)
+_proto("b200_halo_wait_unpack", _i, _vp, C.c_longlong, _vp, _vp, _vp, _sz, _vp, _d)
 _proto("b200_lattice_prolong", _i, _i, _i, _vp, _vp)
 _proto("b200_lattice_restrict", _i, _i, _i, _vp, _vp)
 _proto("b200_cheb_init", _vp, _vp, _vp, _vp, _d, _i, _sz)

@@ -153,10 +153,11 @@ class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
     def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg",
-                 assemble="coo", masked=True, overlap=False):
+                 assemble="coo", masked=True, overlap=False, halo="nccl"):
         """masked: constrained dofs are masked in L-vector-shaped global vectors (no G2L/L2G copies, see LevelDM);
         False: compressed PETSc-style global vectors."""
         self.app, self.dist = app, dist
+        halo_mode = halo
         grid = grid_for(world)
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
         self.mesh = self.gmesh.brick(grid, rank, interface_first=masked and overlap) if world > 1 else self.gmesh
@@ -172,6 +173,8 @@ class Elasticity:
             if world > 1:
                 from .halo import Halo
                 halo = Halo(self.gmesh, grid, rank, deg, dist)
+                if halo_mode == "p2p":
+                    halo.enable_p2p()
             dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}", shared=True,
                                 masked=masked)
             self.dms.append(dm)
@@ -206,6 +209,10 @@ class Elasticity:
         self.V.consistent = {}
         h_dms = build_h_dms(self.gmesh, grid, rank, world, faces, f"cuda:{device_id}", dist, masked=masked) \
             if coarse == "hmg" else None
+        if halo_mode == "p2p":
+            for dm in (h_dms or []):
+                if dm.halo is not None:
+                    dm.halo.enable_p2p()
         for dm in self.dms + list(h_dms or []):
             if dm.dot_weight is not None:
                 self.V.weights[dm.nglobal] = dm.dot_weight

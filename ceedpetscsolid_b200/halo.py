@@ -156,10 +156,80 @@ class Halo:
                 w.wait()
         self._scatter(vec, recv_cat, rbuf, add)
 
+    # ---- sum-and-share over NVLink peer memory (one node): no communication library on the data path
+    def enable_p2p(self, timeout_s=5.0):
+        """Collective over all ranks: allocate this rank's receive window, exchange CUDA IPC handles and segment
+        layouts through torch.distributed (set-up only), map the neighbours' windows.  Afterwards sum_and_share
+        is three kernels of libceed_b200.so (csrc/b200_halo.cu): store the packed partial sums into the
+        neighbours' windows, flag them, wait for the neighbours' flags and add the own window."""
+        import ctypes as C
+        from .ceed import b2, lib
+        dist = self.dist
+        assert self.device.type == "cuda", "peer-memory halo needs CUDA tensors"
+        total = int(self.share_cat.numel())
+        nflags = 64
+        buf = C.c_void_p()
+        nbytes = 2 * total * 8 + nflags * 8 + 8
+        b2(lib.b200_malloc(C.byref(buf), nbytes))
+        b2(lib.b200_memset(buf, 0, nbytes))
+        b2(lib.b200_sync())
+        handle = (C.c_ubyte * 64)()
+        b2(lib.b200_ipc_get_handle(buf, handle))
+        mine = {"rank": self.rank, "handle": bytes(handle), "total": total, "neighbours": list(self.neighbours),
+                "views": {r: self.share_views[r] for r in self.neighbours}}
+        infos = [None] * dist.get_world_size()
+        dist.all_gather_object(infos, mine)
+        nn = len(self.neighbours)
+        seg_start = (C.c_int * (nn + 1))()
+        remote = [(C.c_void_p * max(nn, 1))(), (C.c_void_p * max(nn, 1))()]   # per parity
+        rflag = (C.c_void_p * max(nn, 1))()
+        self._p2p_open = []
+        for s, r in enumerate(self.neighbours):
+            a, b = self.share_views[r]
+            seg_start[s], seg_start[s + 1] = a, b
+            info = infos[r]
+            ra, rb = info["views"][self.rank]
+            assert rb - ra == b - a, "shared sets of a rank pair must have the same size on both sides"
+            base = C.c_void_p()
+            b2(lib.b200_ipc_open((C.c_ubyte * 64).from_buffer_copy(info["handle"]), C.byref(base)))
+            self._p2p_open.append(base)
+            for par in (0, 1):
+                remote[par][s] = base.value + (par * info["total"] + ra) * 8
+            rflag[s] = base.value + 2 * info["total"] * 8 + info["neighbours"].index(self.rank) * 8
+        self._p2p = dict(buf=buf, total=total, nn=nn, seg_start=seg_start, remote=remote, rflag=rflag, gen=0,
+                         flags=buf.value + 2 * total * 8, err=buf.value + 2 * total * 8 + nflags * 8,
+                         timeout=float(timeout_s))
+        dist.barrier()   # every window is mapped before anyone pushes
+
+    def check_p2p(self):
+        """Raises if a peer-memory exchange ever timed out (synchronises the device)."""
+        if getattr(self, "_p2p", None) is None:
+            return
+        import ctypes as C
+        from .ceed import b2, lib
+        e = C.c_int(0)
+        b2(lib.b200_memcpy_d2h(C.byref(e), C.c_void_p(self._p2p["err"]), 4))
+        if e.value:
+            raise RuntimeError("peer-memory halo exchange timed out waiting for a neighbour")
+
+    def _sum_and_share_p2p(self, Yloc):
+        from .ceed import b2, lib
+        p = self._p2p
+        p["gen"] += 1
+        g = p["gen"]
+        par = g & 1
+        b2(lib.b200_halo_push_signal(p["nn"], p["seg_start"], p["remote"][par], p["rflag"], self.share_cat.data_ptr(),
+                                     Yloc.data_ptr(), g))
+        b2(lib.b200_halo_wait_unpack(p["nn"], p["flags"], g, self.share_cat.data_ptr(),
+                                     p["buf"].value + par * p["total"] * 8, Yloc.data_ptr(), p["total"], p["err"],
+                                     p["timeout"]))
+
     def sum_and_share(self, Yloc):
         """One symmetric exchange replacing ghost->owner ADD followed by owner->ghost INSERT: every rank
         sends its partial sums on ALL shared dofs to every sharer and adds what it receives, so all copies
         end up with the assembled value (allowed harness optimisation)."""
+        if getattr(self, "_p2p", None) is not None and Yloc.is_cuda:
+            return self._sum_and_share_p2p(Yloc)
         self._exchange(Yloc, self.share_cat, self.share_views, self.share_cat, self.share_views, add=True, tag="sas")
 
     # ---- split form of sum_and_share: the exchange runs on a side stream while the caller keeps computing on

@@ -187,6 +187,24 @@ int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P,
                         const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
                         const double *d_jcache, double *d_diag);
 
+/* ---- halo exchange over NVLink peer memory (one node, one process per GPU; the DMLocalToGlobal(ADD) +
+ * DMGlobalToLocal(INSERT) pair of matops.c:33,57 as one symmetric sum-and-share, no communication library on the
+ * data path).  Each rank owns a window [parity 0 | parity 1] of packed shared dofs plus one int64 flag per neighbour,
+ * allocated with b200_malloc and exported with CUDA IPC; neighbours store their partial sums into it.
+ *   b200_halo_push_signal: packed position i of segment s (seg_start[s] <= i < seg_start[s+1]) is stored to
+ *                          remote[s][i - seg_start[s]] (peer pointer for this generation's parity), then
+ *                          *remote_flag[s] = gen (release, system scope);
+ *   b200_halo_wait_unpack: waits until d_flags[0..nnbr) >= gen (bounded by timeout_s; on expiry *d_err = 1 and the
+ *                          kernel returns -- loud failure instead of a hung GPU), then y[idx[i]] += window[i]. */
+#define B200_HALO_MAX_NEIGHBOURS 32
+int b200_ipc_get_handle(const void *dptr, unsigned char *handle64);
+int b200_ipc_open(const unsigned char *handle64, void **dptr);
+int b200_ipc_close(void *dptr);
+int b200_halo_push_signal(int nnbr, const int *seg_start, double *const *remote, long long *const *remote_flag,
+                          const int *d_idx, const double *d_y, long long gen);
+int b200_halo_wait_unpack(int nnbr, const long long *d_flags, long long gen, const int *d_idx, const double *d_window,
+                          double *d_y, size_t total, int *d_err, double timeout_s);
+
 /* Host-resident L-vectors (-memtype host; CeedVectorSetArray(HOST) ... TakeArray(HOST), matops.c:40-50): the fused
  * apply as a pipeline  H2D of x chunks | kernel on element chunks | D2H of finished y rows  on three streams.
  * chunk_end[c] = one past the last element of chunk c (multiples of b200_elems_per_block(Q) except the last);

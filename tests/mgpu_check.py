@@ -32,6 +32,9 @@ def main():
     degrees, data, phys = setuplibceed.setup_all(ceed, mesh, problem, p)
     fine = len(degrees) - 1
     halo = Halo(gmesh, grid, rank, p, dist)
+    p2p = os.environ.get("MGPU_HALO", "nccl") == "p2p"
+    if p2p:
+        halo.enable_p2p()
     shared = os.environ.get("MGPU_SHARED", "0") in ("1", "masked")
     masked = os.environ.get("MGPU_SHARED", "0") == "masked"
     dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=shared, masked=masked)
@@ -58,8 +61,10 @@ def main():
     xglob[gbc] = 0.0
     X, Y = dm.create_global_vector(), dm.create_global_vector()
     X.copy_(torch.from_numpy(xglob[mydofs]))
-    matops.ApplyJacobian_Ceed(user, X, Y)
+    for _ in range(5 if p2p else 1):   # several exchanges: generation counters and window parity
+        matops.ApplyJacobian_Ceed(user, X, Y)
     torch.cuda.synchronize()
+    halo.check_p2p()
     # gather (dof id, value) pairs on rank 0
     parts = [None] * world
     dist.all_gather_object(parts, (mydofs, Y.cpu().numpy()))
@@ -77,7 +82,7 @@ def main():
         err = rel_err(ypar[free], yref[free])
         ok = bool(np.all(seen[free] >= 1) and (shared or np.all(seen[free] == 1)) and err < 1e-12
                   and (np.all(ypar[gbc] == 0.0) if masked else np.all(seen[gbc] == 0)))
-        print(f"mgpu_check world={world} bricks={grid} shared={shared} masked={masked}: rel err {err:.2e} -> {'PASS' if ok else 'FAIL'}")
+        print(f"mgpu_check world={world} bricks={grid} shared={shared} masked={masked} halo={'p2p' if p2p else 'nccl'}: rel err {err:.2e} -> {'PASS' if ok else 'FAIL'}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
