@@ -143,6 +143,8 @@ def solve_bench(args, rank, world, local_rank, dist, config):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     clocks = sampler.result()
+    launches = int(libceed.launch_count())
+    energy = el.strain_energy()   # elasticity.c:820-830: printed by the reference after the solve (all ranks: reduction)
     if rank == 0:
         config.update({"workload": f"{args.problem} degree {args.degree} Newton-Krylov-pMG solve, box {args.n}^3 per GPU, "
                                    f"{args.load_steps} load steps, levels {el.degrees}", "elements_per_gpu": el.mesh.nelem,
@@ -152,7 +154,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "snes_its": out["snes_its"], "ksp_its": out["ksp_its"], "converged": out["converged"],
                           "coarse_pcg_its": out["coarse_its"], "coarse_rtol": args.coarse_rtol, "coarse": args.coarse, "assemble": args.assemble, "dofs_unconstrained": out["dofs_global_unconstrained"],
-                          "mdofs_per_sec_in_snes": out["mdofs_per_sec_in_snes"], "gpu_launches": int(libceed.launch_count()),
+                          "mdofs_per_sec_in_snes": out["mdofs_per_sec_in_snes"], "strain_energy": energy, "gpu_launches": launches,
                           "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()

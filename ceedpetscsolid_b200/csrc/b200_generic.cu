@@ -173,6 +173,27 @@ __global__ void k_qfunction(int qf, const __grid_constant__ Material mt, const _
       OUT(0, 3, 2) = -(lam * (u1xz + u2yz + u3zz) + 2 * mu * u3zz + 0.5 * mu * (u3xx + u1xz + u3yy + u2yz)) * w;
       continue;
     }
+    if (qf >= B200_QF_LINELAS_ENERGY && qf <= B200_QF_HYPERFS_DIAG) {
+      // post-processing: energy (du, qdata) -> w psi;  diagnostic (u, du, qdata) -> u, p, I1, I2, J, psi
+      const bool diag = qf >= B200_QF_LINELAS_DIAG;
+      const int kd = diag ? 1 : 0, kq = diag ? 2 : 1;  // field index of du and of qdata
+      double H[3][3], A[3][3], p[5];
+      for (int d = 0; d < 3; d++)
+        for (int c = 0; c < 3; c++) H[c][d] = IN(kd, 9, d * 3 + c);
+      for (int r = 0; r < 3; r++)
+        for (int s = 0; s < 3; s++) A[r][s] = IN(kq, 10, 1 + 3 * r + s);
+      const int prob = (qf - (diag ? B200_QF_LINELAS_DIAG : B200_QF_LINELAS_ENERGY));
+      if (prob == 0) post_point<B200_PROB_LINELAS>(mt, A, H, p);
+      else if (prob == 1) post_point<B200_PROB_HYPERSS>(mt, A, H, p);
+      else post_point<B200_PROB_HYPERFS>(mt, A, H, p);
+      if (diag) {
+        for (int c = 0; c < 3; c++) OUT(0, 8, c) = IN(0, 3, c);
+        for (int c = 0; c < 5; c++) OUT(0, 8, 3 + c) = p[c];
+      } else {
+        OUT(0, 1, 0) = p[4] * IN(kq, 10, 0);
+      }
+      continue;
+    }
     // solid-mechanics point functions: in0 = du [d][c], in1 = qdata[10], (in2 = gradu [c][k])
     double H[3][3], A[3][3], W[3][3], g[3][3];
     for (int d = 0; d < 3; d++)
@@ -285,9 +306,9 @@ extern "C" int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double
 extern "C" int b200_qfunction_apply(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
                                     int nin, const double *const *d_in, int nout, double *const *d_out) {
   if (nin > 4 || nout > 4) return set_error_msg("b200_qfunction_apply: at most 4 input and 4 output fields");
-  if (qf_id <= B200_QF_NONE || qf_id > B200_QF_MMS_TRUE) return set_error_msg("b200_qfunction_apply: unknown QFunction id");
+  if (qf_id <= B200_QF_NONE || qf_id > B200_QF_LAST) return set_error_msg("b200_qfunction_apply: unknown QFunction id");
   const int need_in = (qf_id == B200_QF_IDENTITY || qf_id == B200_QF_MMS_TRUE) ? 1
-                      : (qf_id == B200_QF_HYPERSS_DF || qf_id == B200_QF_HYPERFS_DF) ? 3 : 2;
+                      : (qf_id == B200_QF_HYPERSS_DF || qf_id == B200_QF_HYPERFS_DF || qf_id >= B200_QF_LINELAS_DIAG) ? 3 : 2;
   const int need_out = (qf_id == B200_QF_HYPERSS_F || qf_id == B200_QF_HYPERFS_F) ? 2 : 1;
   if (nin < need_in || nout < need_out) return set_error_msg("b200_qfunction_apply: field count does not match the QFunction");
   QFArgs a;

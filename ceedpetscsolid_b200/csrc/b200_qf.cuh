@@ -11,7 +11,8 @@
 
 namespace b200 {
 
-#define B200_DI __device__ __forceinline__
+// host + device: tests/c/qf_host_check.cu runs the SAME point functions on the CPU against the reference QFunctions
+#define B200_DI __host__ __device__ __forceinline__
 
 B200_DI void phys_grad(const double (&A)[3][3], const double (&H)[3][3], double (&g)[3][3]) {
 #pragma unroll
@@ -220,6 +221,43 @@ B200_DI void hyperfs_df_point_faithful(const Material &mt, double w, const doubl
       dP[a][b] = s * w;
     }
   pull_back(A, dP, W);
+}
+
+// ------------------------------------------------------------------ post-processing
+// Strain energy density and nodal diagnostics (one-shot operators, setuplibceed.c:650-737):
+//   p[0] pressure, p[1] first strain invariant, p[2] second invariant, p[3] volume ratio, p[4] energy density
+// linElas.h:285-478, hyperSS.h:326-528, hyperFS.h:469-668.  The small-strain energies keep the reference's
+// `strain_vol*mu` term as written.
+template <int PROB>
+B200_DI void post_point(const Material &mt, const double (&A)[3][3], const double (&H)[3][3], double (&p)[5]) {
+  double g[3][3];
+  phys_grad(A, H, g);
+  if (PROB == B200_PROB_HYPERFS) {
+    double e[6];
+    const double detC_m1 = green_lagrange2(g, e);  // e = 2E, Voigt (00,11,22,12,02,01)
+    const double logj = log1p_series_shifted(detC_m1) / 2.;
+    const double tr2 = e[0] + e[1] + e[2];
+    p[0] = -mt.lambda * logj;
+    p[1] = tr2 / 2.;
+    p[2] = (e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + 2. * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5])) / 4.;
+    p[3] = sqrt(detC_m1 + 1.);
+    p[4] = mt.lambda * logj * logj / 2. - mt.mu * logj + mt.mu * tr2 / 2.;
+  } else {
+    const double e01 = (g[0][1] + g[1][0]) / 2., e02 = (g[0][2] + g[2][0]) / 2., e12 = (g[1][2] + g[2][1]) / 2.;
+    const double tr = g[0][0] + g[1][1] + g[2][2];
+    const double shear = (e01 * e01 + e02 * e02 + e12 * e12) * 2. * mt.mu;
+    if (PROB == B200_PROB_HYPERSS) {
+      const double llv = log1p_series(tr);
+      p[0] = -mt.lambda * llv;
+      p[4] = mt.lambda * (1. + tr) * (llv - 1.) + tr * mt.mu + shear;
+    } else {
+      p[0] = -mt.lambda * tr;
+      p[4] = mt.lambda * tr * tr / 2. + tr * mt.mu + shear;
+    }
+    p[1] = tr;
+    p[2] = g[0][0] * g[0][0] + g[1][1] * g[1][1] + g[2][2] * g[2][2] + 2. * (e01 * e01 + e02 * e02 + e12 * e12);
+    p[3] = 1. + tr;
+  }
 }
 
 // ------------------------------------------------------------------ Jacobian cache

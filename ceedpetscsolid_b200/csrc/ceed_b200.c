@@ -694,7 +694,10 @@ static int qf_lookup(const char *name) {
       {"SetupGeo", B200_QF_SETUPGEO},     {"LinElasF", B200_QF_LINELAS_F},   {"LinElasdF", B200_QF_LINELAS_DF},
       {"HyperSSF", B200_QF_HYPERSS_F},    {"HyperSSdF", B200_QF_HYPERSS_DF}, {"HyperFSF", B200_QF_HYPERFS_F},
       {"HyperFSdF", B200_QF_HYPERFS_DF},  {"Identity", B200_QF_IDENTITY},    {"SetupConstantForce", B200_QF_CONST_FORCE},
-      {"SetupMMSForce", B200_QF_MMS_FORCE}, {"MMSTrueSoln", B200_QF_MMS_TRUE}, {NULL, 0}};
+      {"SetupMMSForce", B200_QF_MMS_FORCE}, {"MMSTrueSoln", B200_QF_MMS_TRUE},
+      {"LinElasEnergy", B200_QF_LINELAS_ENERGY}, {"HyperSSEnergy", B200_QF_HYPERSS_ENERGY},
+      {"HyperFSEnergy", B200_QF_HYPERFS_ENERGY}, {"LinElasDiagnostic", B200_QF_LINELAS_DIAG},
+      {"HyperSSDiagnostic", B200_QF_HYPERSS_DIAG}, {"HyperFSDiagnostic", B200_QF_HYPERFS_DIAG}, {NULL, 0}};
   for (int i = 0; table[i].n; i++)
     if (!strcmp(table[i].n, name)) return table[i].id;
   return B200_QF_NONE;

@@ -255,6 +255,30 @@ class Elasticity:
         out["mdofs_per_sec_in_snes"] = 1e-6 * out["dofs_global_unconstrained"] * out["ksp_its"] / max(out["time_s"], 1e-12)
         return out
 
+    def strain_energy(self):
+        """elasticity.c:820-830: strain energy of the current state at full load (ComputeStrainEnergy)."""
+        fine = len(self.degrees) - 1
+        if self.data[fine].opEnergy is None:
+            setuplibceed.setup_energy(self.ceed, self.mesh, self.app.problem, self.data[fine], self.phys)
+        self.res_user.loadIncrement = 1.0
+        return matops.ComputeStrainEnergy(self.res_user, self.data[fine].opEnergy, self.U,
+                                          self.dist if self.dist is not None and self.dist.get_world_size() > 1 else None)
+
+    def diagnostic_quantities(self):
+        """elasticity.c:836-850 (ViewDiagnosticQuantities without the VTK writer): (local nodes, 8) tensor =
+        displacement, pressure, two strain invariants, volume ratio, energy density."""
+        fine = len(self.degrees) - 1
+        d = self.data[fine]
+        if d.opDiagnostic is None:
+            setuplibceed.setup_diagnostic(self.ceed, self.mesh, self.app.problem, d, self.phys)
+        halo8 = None
+        if self.dms[fine].halo is not None:
+            from .halo import Halo
+            h = self.dms[fine].halo
+            halo8 = Halo(self.gmesh, h.grid, h.rank, h.p, h.dist, ncomp=8)
+        self.res_user.loadIncrement = 1.0
+        return matops.ComputeDiagnosticQuantities(self.res_user, d.opDiagnostic, d.ErestrictDiagnostic, self.U, halo8)
+
     def mms_l2_error(self):
         """elasticity.c:770-816: |U - U_true| / |U| over the global (unconstrained) dofs."""
         fine = len(self.degrees) - 1

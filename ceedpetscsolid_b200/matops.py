@@ -260,6 +260,58 @@ def GetDiag_Ceed(user, D):
     user.Xloc.zero_()
 
 
+def _state_lvector(X, user):
+    """Xloc = [free dofs of X; boundary values at user.loadIncrement] (VecZeroEntries, DMGlobalToLocal,
+    DMPlexInsertBoundaryValues: matops.c:258-262, misc.c:243-247)."""
+    user.dm.zero_and_global_to_local(X, user.Xloc)
+    if user.bc_values is not None:
+        user.dm.insert_boundary_values(user.Xloc, user.bc_values(user.loadIncrement))
+    return user.Xloc
+
+
+def ComputeStrainEnergy(user, opEnergy, X, dist=None):
+    """matops.c:247-300: strain energy of the state X = sum of the entries of E_e^T B_e^T [w detJ psi] (one scalar
+    per mesh node), summed over ranks."""
+    xloc = _state_lvector(X, user)
+    nn = user.dm.lsize // 3
+    eloc = user.ceed.Vector(nn)
+    user.Xceed.set_array(xloc, user.memType, USE_POINTER)
+    opEnergy.apply(user.Xceed, eloc)
+    user.Xceed.take_array(user.memType)
+    energy = float(eloc.to_numpy().sum())          # CeedVectorGetArrayRead(HOST) + host loop, matops.c:285-290
+    eloc.destroy()
+    if dist is not None and dist.get_world_size() > 1:
+        t = torch.tensor([energy], dtype=torch.float64, device=user.dm.device)
+        dist.all_reduce(t)
+        energy = float(t.item())
+    return energy
+
+
+def ComputeDiagnosticQuantities(user, opDiagnostic, ErestrictDiagnostic, X, halo8=None):
+    """ViewDiagnosticQuantities (src/misc.c:217-300) without the VTK writer: nodal (u, pressure, two strain
+    invariants, volume ratio, energy density), element contributions summed and divided by the node multiplicity.
+    halo8: a Halo built with ncomp=8 for partitioned runs (interface nodes get contributions from every rank).
+    Returns a (nodes, 8) tensor on the level's device."""
+    xloc = _state_lvector(X, user)
+    nn = user.dm.lsize // 3
+    yloc = torch.zeros(8 * nn, dtype=torch.float64, device=xloc.device)
+    mult = torch.zeros_like(yloc)
+    yc = user.ceed.Vector(8 * nn)
+    user.Xceed.set_array(xloc, user.memType, USE_POINTER)
+    yc.set_array(yloc, user.memType, USE_POINTER)
+    opDiagnostic.apply(user.Xceed, yc)
+    user.Xceed.take_array(user.memType)
+    yc.take_array(user.memType)
+    yc.set_array(mult, user.memType, USE_POINTER)
+    ErestrictDiagnostic.get_multiplicity(yc)
+    yc.take_array(user.memType)
+    yc.destroy()
+    if halo8 is not None:
+        halo8.sum_and_share(yloc)
+        halo8.sum_and_share(mult)
+    return (yloc / mult).reshape(nn, 8)
+
+
 @dataclass
 class UserMultProlongRestr:
     """elasticity.h:202-215; SetupProlongRestrictCtx (src/misc.c:73-146)."""

@@ -20,11 +20,14 @@ from .ceed import (BASIS_COLLOCATED, ELEMRESTRICTION_NONE, EVAL_GRAD, EVAL_INTER
 # problemOptions[] (setuplibceed.c:41-107): qdatasize, residual / Jacobian QFunction locators
 PROBLEM_OPTIONS = {
     "linElas": dict(qdatasize=10, setupgeo="qfunctions/common.h:SetupGeo", apply="qfunctions/linElas.h:LinElasF",
-                    jacob="qfunctions/linElas.h:LinElasdF", qmode=GAUSS, nonlinear=False),
+                    jacob="qfunctions/linElas.h:LinElasdF", qmode=GAUSS, nonlinear=False,
+                    energy="qfunctions/linElas.h:LinElasEnergy", diagnostic="qfunctions/linElas.h:LinElasDiagnostic"),
     "hyperSS": dict(qdatasize=10, setupgeo="qfunctions/common.h:SetupGeo", apply="qfunctions/hyperSS.h:HyperSSF",
-                    jacob="qfunctions/hyperSS.h:HyperSSdF", qmode=GAUSS, nonlinear=True),
+                    jacob="qfunctions/hyperSS.h:HyperSSdF", qmode=GAUSS, nonlinear=True,
+                    energy="qfunctions/hyperSS.h:HyperSSEnergy", diagnostic="qfunctions/hyperSS.h:HyperSSDiagnostic"),
     "hyperFS": dict(qdatasize=10, setupgeo="qfunctions/common.h:SetupGeo", apply="qfunctions/hyperFS.h:HyperFSF",
-                    jacob="qfunctions/hyperFS.h:HyperFSdF", qmode=GAUSS, nonlinear=True),
+                    jacob="qfunctions/hyperFS.h:HyperFSdF", qmode=GAUSS, nonlinear=True,
+                    energy="qfunctions/hyperFS.h:HyperFSEnergy", diagnostic="qfunctions/hyperFS.h:HyperFSDiagnostic"),
 }
 
 
@@ -61,6 +64,17 @@ class CeedData:
     gradu: object = None
     xceed: object = None
     yceed: object = None
+    # post-processing (setuplibceed.c:645-737)
+    ErestrictEnergy: object = None
+    basisEnergy: object = None
+    qfEnergy: object = None
+    opEnergy: object = None
+    ErestrictDiagnostic: object = None
+    ErestrictqdDiagnostici: object = None
+    basisDiagnostic: object = None
+    qdataDiagnostic: object = None
+    qfDiagnostic: object = None
+    opDiagnostic: object = None
     keep: list = field(default_factory=list)
 
 
@@ -154,6 +168,63 @@ def setup_forcing(ceed, mesh, data, forcing, phys, forcing_vector, force_ceed):
     op.set_field("force", d.Erestrictu, d.basisu, VECTOR_ACTIVE)
     op.apply(xcoord, force_ceed)
     op.destroy(); qf.destroy(); xcoord.destroy()
+
+
+def setup_energy(ceed, mesh, problem, data, phys, node_perm=None):
+    """Strain-energy operator (setuplibceed.c:645-670): energy_L = E_e^T B_e^T [ w detJ psi(grad u) ], one scalar dof per
+    mesh node (dmEnergy, ncompe = 1); ComputeStrainEnergy sums the entries."""
+    d, opt = data, PROBLEM_OPTIONS[problem]
+    P, Q = d.basisu.P, d.basisu.Q
+    d.ErestrictEnergy = create_restriction(ceed, mesh, P, 1, node_perm)
+    d.basisEnergy = ceed.BasisTensorH1Lagrange(3, 1, P, Q, opt["qmode"])
+    d.qfEnergy = ceed.QFunction(1, opt["energy"])
+    d.qfEnergy.add_input("du", 9, EVAL_GRAD)
+    d.qfEnergy.add_input("qdata", opt["qdatasize"], EVAL_NONE)
+    d.qfEnergy.add_output("energy", 1, EVAL_INTERP)
+    d.qfEnergy.set_context(phys)
+    d.opEnergy = ceed.Operator(d.qfEnergy)
+    d.opEnergy.set_field("du", d.Erestrictu, d.basisu, VECTOR_ACTIVE)
+    d.opEnergy.set_field("qdata", d.Erestrictqdi, BASIS_COLLOCATED, d.qdata)
+    d.opEnergy.set_field("energy", d.ErestrictEnergy, d.basisEnergy, VECTOR_ACTIVE)
+    return d.opEnergy
+
+
+def setup_diagnostic(ceed, mesh, problem, data, phys, node_perm=None):
+    """Nodal diagnostic operator (setuplibceed.c:672-737): geometric factors collocated at the GLL nodes
+    (basis P -> P, CEED_GAUSS_LOBATTO), then (u, grad u, qdata) -> 8 values per node, EVAL_NONE out."""
+    d, opt = data, PROBLEM_OPTIONS[problem]
+    P = d.basisu.P
+    nelem, qdatasize = mesh.nelem, opt["qdatasize"]
+    d.ErestrictDiagnostic = create_restriction(ceed, mesh, P, 8, node_perm)
+    d.ErestrictqdDiagnostici = ceed.StridedElemRestriction(nelem, P ** 3, qdatasize, qdatasize * nelem * P ** 3)
+    d.basisDiagnostic = ceed.BasisTensorH1Lagrange(3, 3, P, P, GAUSS_LOBATTO)
+    d.qdataDiagnostic = ceed.Vector(qdatasize * nelem * P ** 3)
+    basisx = ceed.BasisTensorH1Lagrange(3, 3, 2, P, GAUSS_LOBATTO)
+    qfSetupGeo = ceed.QFunction(1, opt["setupgeo"])
+    qfSetupGeo.add_input("dx", 9, EVAL_GRAD)
+    qfSetupGeo.add_input("weight", 1, EVAL_WEIGHT)
+    qfSetupGeo.add_output("qdata", qdatasize, EVAL_NONE)
+    opSetupGeo = ceed.Operator(qfSetupGeo)
+    opSetupGeo.set_field("dx", d.Erestrictx, basisx, VECTOR_ACTIVE)
+    opSetupGeo.set_field("weight", ELEMRESTRICTION_NONE, basisx, VECTOR_NONE)
+    opSetupGeo.set_field("qdata", d.ErestrictqdDiagnostici, BASIS_COLLOCATED, VECTOR_ACTIVE)
+    xcoord = d.Erestrictx.create_vector()
+    xcoord.set_array(mesh.coord_lvector(), libceed.MEM_HOST, libceed.COPY_VALUES)
+    opSetupGeo.apply(xcoord, d.qdataDiagnostic)
+    for o in (basisx, qfSetupGeo, opSetupGeo, xcoord):
+        o.destroy()
+    d.qfDiagnostic = ceed.QFunction(1, opt["diagnostic"])
+    d.qfDiagnostic.add_input("u", 3, EVAL_INTERP)
+    d.qfDiagnostic.add_input("du", 9, EVAL_GRAD)
+    d.qfDiagnostic.add_input("qdata", qdatasize, EVAL_NONE)
+    d.qfDiagnostic.add_output("diagnostic", 8, EVAL_NONE)
+    d.qfDiagnostic.set_context(phys)
+    d.opDiagnostic = ceed.Operator(d.qfDiagnostic)
+    d.opDiagnostic.set_field("u", d.Erestrictu, d.basisDiagnostic, VECTOR_ACTIVE)
+    d.opDiagnostic.set_field("du", d.Erestrictu, d.basisDiagnostic, VECTOR_ACTIVE)
+    d.opDiagnostic.set_field("qdata", d.ErestrictqdDiagnostici, BASIS_COLLOCATED, d.qdataDiagnostic)
+    d.opDiagnostic.set_field("diagnostic", d.ErestrictDiagnostic, BASIS_COLLOCATED, VECTOR_ACTIVE)
+    return d.opDiagnostic
 
 
 def setup_true_solution(ceed, mesh, data, P):

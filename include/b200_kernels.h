@@ -40,7 +40,16 @@ enum {
   B200_QF_IDENTITY,    /* libCEED gallery "Identity" */
   B200_QF_CONST_FORCE, /* qfunctions/constantForce.h:39   SetupConstantForce */
   B200_QF_MMS_FORCE,   /* qfunctions/manufacturedForce.h:39 SetupMMSForce    */
-  B200_QF_MMS_TRUE     /* qfunctions/manufacturedTrue.h:30  MMSTrueSoln      */
+  B200_QF_MMS_TRUE,    /* qfunctions/manufacturedTrue.h:30  MMSTrueSoln      */
+  /* one-shot post-processing (setuplibceed.c:650-737): in = (du GRAD, qdata) -> energy (1);
+   * in = (u INTERP, du GRAD, qdata) -> diagnostic (8) = u, pressure, 2 invariants, volume ratio, energy density */
+  B200_QF_LINELAS_ENERGY,  /* qfunctions/linElas.h:285 */
+  B200_QF_HYPERSS_ENERGY,  /* qfunctions/hyperSS.h:326 */
+  B200_QF_HYPERFS_ENERGY,  /* qfunctions/hyperFS.h:469 */
+  B200_QF_LINELAS_DIAG,    /* qfunctions/linElas.h:376 */
+  B200_QF_HYPERSS_DIAG,    /* qfunctions/hyperSS.h:418 */
+  B200_QF_HYPERFS_DIAG,    /* qfunctions/hyperFS.h:559 */
+  B200_QF_LAST = B200_QF_HYPERFS_DIAG
 };
 
 /* Physics_private {nu, E}  /root/reference/elasticity.h:30-37 */

@@ -368,3 +368,91 @@ int port_SetupMMSForce(void *ctx, int Q, const double *const *in, double *const 
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------- strain energy and nodal diagnostics
+ * (one-shot post-processing operators, setuplibceed.c:650-737).  Point quantities
+ *   p[0] pressure, p[1] first strain invariant, p[2] second invariant, p[3] volume ratio, p[4] energy density
+ * restated from linElas.h:285-478, hyperSS.h:326-528, hyperFS.h:469-668; the small-strain energy keeps the
+ * reference's `strain_vol*mu` term as written. */
+static void post_small_strain(int hyper, double lambda, double mu, const M3 g, double p[5]) {
+  M3 e;
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) e[a][b] = (g[a][b] + g[b][a]) / 2.;
+  const double tr = e[0][0] + e[1][1] + e[2][2];
+  const double shear = (e[0][1] * e[0][1] + e[0][2] * e[0][2] + e[1][2] * e[1][2]) * 2 * mu;
+  double ee = 0;
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) ee += e[a][b] * e[b][a];
+  if (hyper) {
+    const double llv = series_log1p(tr);
+    p[0] = -lambda * llv;
+    p[4] = lambda * (1 + tr) * (llv - 1) + tr * mu + shear;
+  } else {
+    p[0] = -lambda * tr;
+    p[4] = lambda * tr * tr / 2. + tr * mu + shear;
+  }
+  p[1] = tr;
+  p[2] = ee;
+  p[3] = 1 + tr;
+}
+
+static void post_finite_strain(double lambda, double mu, const M3 g, double p[5]) {
+  double e2v[6];
+  for (int m = 0; m < 6; m++) {
+    const int j = VJ[m], k = VK[m];
+    double s = g[j][k] + g[k][j];
+    for (int n = 0; n < 3; n++) s += g[n][j] * g[n][k];
+    e2v[m] = s;
+  }
+  M3 E2;
+  voigt_to_sym(e2v, E2);
+  const double detC_m1 = det_c_minus_1(e2v);
+  const double logj = series_log1p_shifted(detC_m1) / 2.;
+  const double trE2 = E2[0][0] + E2[1][1] + E2[2][2];
+  double ee = 0;
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) ee += E2[a][b] * E2[b][a] / 4.;
+  p[0] = -lambda * logj;
+  p[1] = trE2 / 2.;
+  p[2] = ee;
+  p[3] = sqrt(detC_m1 + 1);
+  p[4] = lambda * logj * logj / 2. - mu * logj + mu * trE2 / 2.;
+}
+
+/* kind: 0 linElas, 1 hyperSS, 2 hyperFS;  du = GRAD input, qd = qdata */
+static void post_point(int kind, const PortPhysics *ph, const double *du, const double *qd, int Q, int i,
+                       double *wdetJ, double p[5]) {
+  double TwoMu, mu, lambda;
+  lame(ph, &TwoMu, &mu, &lambda);
+  M3 dXdx, g;
+  load_qdata(qd, Q, i, wdetJ, dXdx);
+  phys_grad(du, dXdx, Q, i, g);
+  if (kind == 2) post_finite_strain(lambda, mu, g, p);
+  else post_small_strain(kind, lambda, mu, g, p);
+}
+
+static int energy_common(int kind, void *ctx, int Q, const double *const *in, double *const *out) {
+  for (int i = 0; i < Q; i++) {
+    double w, p[5];
+    post_point(kind, (const PortPhysics *)ctx, in[0], in[1], Q, i, &w, p);
+    out[0][i] = p[4] * w;
+  }
+  return 0;
+}
+
+static int diagnostic_common(int kind, void *ctx, int Q, const double *const *in, double *const *out) {
+  for (int i = 0; i < Q; i++) {
+    double w, p[5];
+    post_point(kind, (const PortPhysics *)ctx, in[1], in[2], Q, i, &w, p);
+    for (int c = 0; c < 3; c++) out[0][c * Q + i] = in[0][c * Q + i];
+    for (int c = 0; c < 5; c++) out[0][(3 + c) * Q + i] = p[c];
+  }
+  return 0;
+}
+
+int port_LinElasEnergy(void *ctx, int Q, const double *const *in, double *const *out) { return energy_common(0, ctx, Q, in, out); }
+int port_HyperSSEnergy(void *ctx, int Q, const double *const *in, double *const *out) { return energy_common(1, ctx, Q, in, out); }
+int port_HyperFSEnergy(void *ctx, int Q, const double *const *in, double *const *out) { return energy_common(2, ctx, Q, in, out); }
+int port_LinElasDiagnostic(void *ctx, int Q, const double *const *in, double *const *out) { return diagnostic_common(0, ctx, Q, in, out); }
+int port_HyperSSDiagnostic(void *ctx, int Q, const double *const *in, double *const *out) { return diagnostic_common(1, ctx, Q, in, out); }
+int port_HyperFSDiagnostic(void *ctx, int Q, const double *const *in, double *const *out) { return diagnostic_common(2, ctx, Q, in, out); }
