@@ -125,9 +125,18 @@ def solve_bench(args, rank, world, local_rank, dist, config):
     grid = grid_for(world)
     n = (args.n * grid[0], args.n * grid[1], args.n * grid[2]) if args.scaling == "weak" else (args.n,) * 3
     lengths = tuple(float(g) for g in grid) if args.scaling == "weak" else (1.0, 1.0, 1.0)
+    umesh = None
+    if args.mesh:
+        from ceedpetscsolid_b200.exodus import HexMesh, tube_mesh
+        umesh = tube_mesh(*[int(v) for v in args.mesh[5:].split(",")]) if args.mesh.startswith("tube:") else HexMesh.from_file(args.mesh)
     app = AppCtx(problem=args.problem, degree=args.degree, n=n, num_steps=args.load_steps, perturb=0.05,
                  clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1 * lengths[2], 0, 0, 1, 0]})
     gmesh = BoxMesh(n=n, perturb=app.perturb, seed=0, lengths=lengths)
+    if umesh is not None:
+        ids = [int(v) for v in args.clamp_sets.split(",")]
+        ext = float(np.ptp(umesh.vertices, axis=0).max())
+        app.mesh, gmesh = umesh, None
+        app.clamp = {ids[0]: [0, 0, 0, 0, 0, 1, 0], ids[1]: [0, -0.05 * ext, 0.1 * ext, 0, 0, 1, 0]}
     el = Elasticity(app, dist=dist if world > 1 else None, rank=rank, world=world, device_id=local_rank, gmesh=gmesh,
                     coarse_rtol=args.coarse_rtol, coarse=args.coarse, assemble=args.assemble, masked=args.dm == "masked",
                     halo=args.halo)
@@ -147,7 +156,8 @@ def solve_bench(args, rank, world, local_rank, dist, config):
     energy = el.strain_energy()   # elasticity.c:820-830: printed by the reference after the solve (all ranks: reduction)
     if rank == 0:
         config.update({"workload": f"{args.problem} degree {args.degree} Newton-Krylov-pMG solve, box {args.n}^3 per GPU, "
-                                   f"{args.load_steps} load steps, levels {el.degrees}", "elements_per_gpu": el.mesh.nelem,
+                                   f"{args.load_steps} load steps, levels {el.degrees}" + (f", mesh {args.mesh}" if args.mesh else ""),
+                       "elements_per_gpu": el.mesh.nelem,
                        "bricks": "x".join(map(str, grid))})
         print(json.dumps({"metric": "SNES solve time", "value": float(t.item()), "unit": "s", "n_gpus": world, "steps": 1,
                           "warmup": 0, "ms_per_step": float(t.item()) * 1e3, "higher_is_better": False,
@@ -176,6 +186,9 @@ def main():
     ap.add_argument("--solve", action="store_true",
                     help="time the full Newton-Krylov-p-MG solve (BASELINE configs[4]) instead of the MatMult")
     ap.add_argument("--load-steps", type=int, default=10)
+    ap.add_argument("--mesh", default=None, help="--solve on an unstructured hex8 mesh: an Exodus II file (-mesh, "
+                    "setupdm.c:40-68) or 'tube:NR,NT,NZ' (synthetic); side sets --clamp-sets are clamped")
+    ap.add_argument("--clamp-sets", default="1,2", help="side-set ids: first fixed, second translated by (0,-0.05,0.1) x length scale")
     ap.add_argument("--coarse-rtol", type=float, default=1e-2)
     ap.add_argument("--coarse-maxit", type=int, default=500)
     ap.add_argument("--dm", default="masked", choices=["masked", "compressed"],

@@ -59,6 +59,8 @@ class AppCtx:
     test_mode: bool = False        # -test: MMS forcing, BCMMS on every boundary face (cloptions.c:185-187, setupdm.c:160-170)
     # clamped faces: (axis, side) -> [tx,ty,tz, kx,ky,kz, theta/pi]  (-bc_clamp, -bc_clamp_N_translate/_rotate)
     clamp: dict = field(default_factory=lambda: {(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0, 0, -0.1, 0, 0, 1, 0]})
+    # -mesh file.exo (setupdm.c:40-68): an exodus.HexMesh; `clamp` is then keyed by side-set id (-bc_clamp 998,999)
+    mesh: object = None
 
 
 def build_h_dms(gmesh, grid, rank, world, faces, device, dist=None, min_elems=2, masked=False):
@@ -159,6 +161,10 @@ class Elasticity:
         self.app, self.dist = app, dist
         halo_mode = halo
         grid = grid_for(world)
+        if app.mesh is not None:
+            if world > 1:
+                raise NotImplementedError("partitioned runs need a brick-partitioned box mesh; -mesh files run on one GPU")
+            gmesh = app.mesh
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
         self.mesh = self.gmesh.brick(grid, rank, interface_first=masked and overlap) if world > 1 else self.gmesh
         self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}")
@@ -208,7 +214,7 @@ class Elasticity:
         self.V = solver.Vec(dist if world > 1 else None)
         self.V.consistent = {}
         h_dms = build_h_dms(self.gmesh, grid, rank, world, faces, f"cuda:{device_id}", dist, masked=masked) \
-            if coarse == "hmg" else None
+            if coarse == "hmg" and getattr(self.gmesh, "structured", True) else None
         if halo_mode == "p2p":
             for dm in (h_dms or []):
                 if dm.halo is not None:
@@ -231,8 +237,8 @@ class Elasticity:
         if app.test_mode:
             return lambda load: torch.from_numpy(bc_mms(xyz, load).reshape(-1)).to(dm.device)
         face_of = np.full(bc_nodes.size, -1)
-        for fi, (axis, side) in enumerate(app.clamp.keys()):  # later faces win on shared edges, as DMAddBoundary order
-            on = dm.mesh.boundary_mask(p, [(axis, side)])[bc_nodes]
+        for fi, face in enumerate(app.clamp.keys()):  # later faces win on shared edges, as DMAddBoundary order
+            on = dm.mesh.boundary_mask(p, [face])[bc_nodes]
             face_of[on] = fi
         clamps = list(app.clamp.values())
 

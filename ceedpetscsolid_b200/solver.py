@@ -475,6 +475,80 @@ class ColoredCoarseMatrix:
         self.dm.fix_diagonal(D)
 
 
+class SparseCoarseMatrix:
+    """The assembled p = 1 Jacobian on an UNSTRUCTURED mesh (-mesh file.exo): no node lattice, so the matrix is kept
+    in ELL form (slot-major, b200_ell_spmv).  Filled from the CeedOperatorLinearAssemble element matrices (device),
+    or -- CPU tensors, small oracle-driven tests only -- by probing the local operator with unit vectors."""
+
+    def __init__(self, dm, local_apply, coo=None):
+        self.dm, self.local_apply, self.coo = dm, local_apply, coo
+        n, dev = dm.lsize, dm.device
+        self.Xloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.Yloc = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.dense = None
+        if coo is not None:
+            nodes = coo.elem_nodes.long()                                        # (E, 8)
+            dof = (nodes[:, :, None] * 3 + torch.arange(3, device=nodes.device)[None, None, :]).reshape(-1, 24)
+            rows = dof[:, None, :].expand(-1, 24, -1).reshape(-1)                # values layout [e][col][row]
+            cols = dof[:, :, None].expand(-1, -1, 24).reshape(-1)
+            uniq, inv = torch.unique(rows * n + cols, return_inverse=True)       # sorted by row, then column
+            r, c = uniq // n, uniq % n
+            start = torch.searchsorted(r, torch.arange(n, device=r.device))
+            slot = torch.arange(uniq.numel(), device=r.device) - start[r]
+            self.nslots = int(slot.max().item()) + 1
+            ell = slot * n + r
+            self.cols = torch.full((self.nslots * n,), -1, dtype=torch.int32, device=dev)
+            self.cols[ell] = c.to(torch.int32)
+            self.vals = torch.zeros(self.nslots * n, dtype=torch.float64, device=dev)
+            self.dest = ell[inv]
+            self.diag_pos = ell[r == c]                                          # one per row, in row order
+
+    def assemble(self):
+        if self.coo is not None:
+            self.vals.zero_()
+            self.vals.index_add_(0, self.dest, self.coo.values())
+            return
+        n = self.dm.lsize
+        A = torch.zeros((n, n), dtype=torch.float64)
+        e = torch.zeros(n, dtype=torch.float64)
+        y = torch.zeros(n, dtype=torch.float64)
+        for j in range(n):
+            e.zero_()
+            e[j] = 1.0
+            self.local_apply(e, y)
+            A[:, j] = y
+        self.dense = A
+
+    def local_mult(self, xloc, yloc):
+        if self.dense is not None:
+            torch.mv(self.dense, xloc, out=yloc)
+        elif not xloc.is_cuda:
+            n = self.dm.lsize
+            c = self.cols.view(self.nslots, n).long()
+            yloc.copy_((self.vals.view(self.nslots, n) * xloc[c.clamp_min(0)] * (c >= 0)).sum(0))
+        else:
+            b2(lib.b200_ell_spmv(self.dm.lsize, self.nslots, self.cols.data_ptr(), self.vals.data_ptr(), xloc.data_ptr(),
+                                 yloc.data_ptr()))
+
+    def mult(self, X, Y):
+        dm = self.dm
+        if dm.masked:
+            self.local_mult(X, Y)
+            dm.local_to_global(Y, Y)
+            return
+        dm.zero_and_global_to_local(X, self.Xloc)
+        self.local_mult(self.Xloc, self.Yloc)
+        dm.local_to_global(self.Yloc, Y)
+
+    def diagonal(self, D):
+        if self.dense is not None:
+            self.Yloc.copy_(torch.diagonal(self.dense))
+        else:
+            self.Yloc.copy_(self.vals[self.diag_pos])
+        self.dm.local_to_global(self.Yloc, D)
+        self.dm.fix_diagonal(D)
+
+
 class HMultigrid:
     """Geometric h-multigrid on the assembled p = 1 level: the stand-in for GAMG (elasticity.c:569-585).
 
@@ -637,7 +711,8 @@ class PMultigrid:
         self.r = [mk(l) for l in range(L)]
         self.t = [mk(l) for l in range(L)]
         self.diag = [mk(l) for l in range(L)]
-        self.coarse = ColoredCoarseMatrix(levels[0].dm, levels[0].local_apply, coo=getattr(levels[0], "coo", None))
+        CoarseMatrix = ColoredCoarseMatrix if getattr(levels[0].dm.mesh, "structured", True) else SparseCoarseMatrix
+        self.coarse = CoarseMatrix(levels[0].dm, levels[0].local_apply, coo=getattr(levels[0], "coo", None))
         # h_dms: LevelDMs of successively halved meshes below the p = 1 level -> geometric multigrid coarse
         # solve (GAMG stand-in); None -> Jacobi-PCG on the assembled p = 1 matrix
         self.hmg = HMultigrid(V, self.coarse, [levels[0].dm] + list(h_dms)) if h_dms else None

@@ -14,10 +14,10 @@ def dev(a):
 
 class GpuProblem:
     def __init__(self, problem, n, p, perturb=0.08, qextra=0, scale=0.02, multigrid="logarithmic",
-                 node_perm_seed=None, nu=0.3, E=1.0):
+                 node_perm_seed=None, nu=0.3, E=1.0, mesh=None):
         n = (n, n, n) if np.isscalar(n) else n
         self.problem, self.p, self.qextra = problem, p, qextra
-        self.mesh = BoxMesh(n=n, perturb=perturb, seed=0)
+        self.mesh = mesh if mesh is not None else BoxMesh(n=n, perturb=perturb, seed=0)
         self.ceed = libceed.Ceed("/gpu/b200")
         self.perm = None
         if node_perm_seed is not None:

@@ -11,11 +11,11 @@ class OracleProblem:
     """Box problem at fine degree `p` with level degree `pl` (P = pl+1, Q = p+1+qextra)."""
 
     def __init__(self, problem, n, p, pl=None, perturb=0.08, qextra=0, scale=0.02, which=None,
-                 node_perm_seed=None):
+                 node_perm_seed=None, mesh=None):
         self.problem, self.p, self.pl = problem, p, (p if pl is None else pl)
         self.which = which
         n = (n, n, n) if np.isscalar(n) else n
-        self.mesh = BoxMesh(n=n, perturb=perturb, seed=0)
+        self.mesh = mesh if mesh is not None else BoxMesh(n=n, perturb=perturb, seed=0)
         self.nelem = self.mesh.nelem
         self.P, self.Pf, self.Q = self.pl + 1, p + 1, p + 1 + qextra
         self.perm = None

@@ -12,7 +12,7 @@ from oracle import oracle
 class OracleShared:
     def __init__(self, app, masked=False):
         self.app, self.masked = app, masked
-        self.mesh = BoxMesh(n=app.n, perturb=app.perturb, seed=0)
+        self.mesh = app.mesh if getattr(app, "mesh", None) is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
         self.degrees = setuplibceed.level_degrees(app.degree, app.multigrid)
         p = app.degree
         self.Q = p + 1 + app.qextra
@@ -101,7 +101,8 @@ def oracle_solve(app, log=None, coarse="hmg", masked=True, **kw):
     V = solver.Vec(None)
     V.consistent = {}
     faces = "all" if app.test_mode else list(app.clamp.keys())
-    h_dms = build_h_dms(sh.mesh, (1, 1, 1), 0, 1, faces, "cpu", masked=masked) if coarse == "hmg" else None
+    h_dms = build_h_dms(sh.mesh, (1, 1, 1), 0, 1, faces, "cpu", masked=masked) \
+        if coarse == "hmg" and getattr(sh.mesh, "structured", True) else None
     if masked:
         for dm in [lev.dm for lev in levels] + list(h_dms or []):
             V.consistent[dm.nglobal] = dm.make_consistent
