@@ -341,6 +341,20 @@ def main():
                 "kernel_ms": kms, "algorithmic_bytes_per_launch": ab,
                 "algorithmic_bytes_per_element": alg_bytes(problem, p),
                 "kernel_gdofs": 3 * mesh.num_nodes(p) / (kms * 1e-3) / 1e9}
+    # FP64 cross-check: DFMA-class instructions the kernel executes per element (12 line stages x
+    # 3 Q^4 + Q^3 x ~105 for the cached hyperFS Jacobian) against a DFMA microbenchmark run now
+    if problem == "hyperFS" and p == 4:
+        try:
+            import ctypes as C
+            rate = C.c_double(0.0)
+            libceed.b2(libceed.lib.b200_fp64_probe(C.byref(rate)))
+            Qn = p + 1
+            dfma_elem = 12 * 3 * Qn ** 4 + Qn ** 3 * 105
+            roofline["fp64"] = {"dfma_per_element": dfma_elem, "kernel_tdfma_per_s": dfma_elem * mesh.nelem / (kms * 1e-3) / 1e12,
+                                "probe_tdfma_per_s": rate.value / 1e12,
+                                "frac": dfma_elem * mesh.nelem / (kms * 1e-3) / rate.value}
+        except Exception as exc:  # the probe is informational: never fail the bench on it
+            roofline["fp64"] = {"error": str(exc)}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         with open(traffic_path) as f:

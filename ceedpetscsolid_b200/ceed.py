@@ -140,6 +140,7 @@ _proto("b200_vec_aypx_dev", _vp, _vp, _sz, _vp, _vp)
 _proto("b200_pcg_update", _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp)
 _proto("b200_stencil27_spmv", _i, _i, _i, _vp, _vp, _vp)
 _proto("b200_stencil27_galerkin", _i, _i, _i, _vp, _vp)
+_proto("b200_fp64_probe", C.POINTER(_d))
 _proto("b200_ipc_get_handle", _vp, _vp)
 _proto("b200_ipc_open", _vp, _pvp)
 _proto("b200_ipc_close", _vp)

@@ -166,6 +166,16 @@ __global__ void k_ell_spmv(size_t n, int nslots, const int *__restrict__ cols, c
     y[r] = s;
   }
 }
+__global__ void k_fp64_probe(double *sink, int iters, double m) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  sink[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
 __global__ void k_fill_strided(double *d, double v, size_t n, size_t stride, size_t count) {
   GRID_STRIDE(i, n * count) d[(i / n) * stride + i % n] = v;
 }
@@ -424,6 +434,29 @@ int b200_apply_hostpipe(int jacobian, int problem, const b200_physics *phys, int
   }
   B200_CHECK(cudaStreamSynchronize(s_out));  // the libCEED call is synchronous for host-visible results
   B200_CHECK(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+// FP64 pipe probe ("measure with a DFMA microbenchmark"): 8 independent DFMA chains per thread.
+int b200_fp64_probe(double *dfma_per_second) {
+  const int iters = 4096, nblk = 148 * 16, nthr = 256;
+  double *sink = nullptr;
+  B200_CHECK(cudaMalloc(&sink, sizeof(double) * nblk * nthr));
+  cudaEvent_t e0, e1;
+  B200_CHECK(cudaEventCreate(&e0));
+  B200_CHECK(cudaEventCreate(&e1));
+  k_fp64_probe<<<nblk, nthr, 0, g_stream>>>(sink, iters, 1.0000001);   // warm-up
+  B200_CHECK(cudaEventRecord(e0, g_stream));
+  for (int r = 0; r < 4; r++) k_fp64_probe<<<nblk, nthr, 0, g_stream>>>(sink, iters, 1.0000001);
+  B200_CHECK(cudaEventRecord(e1, g_stream));
+  B200_CHECK(cudaEventSynchronize(e1));
+  B200_LAUNCH_CHECK("k_fp64_probe");
+  float ms = 0;
+  B200_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  *dfma_per_second = 4.0 * 8.0 * iters * (double)nblk * nthr / (ms * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  B200_CHECK(cudaFree(sink));
   return 0;
 }
 

@@ -214,6 +214,10 @@ int b200_halo_push_signal(int nnbr, const int *seg_start, double *const *remote,
 int b200_halo_wait_unpack(int nnbr, const long long *d_flags, long long gen, const int *d_idx, const double *d_window,
                           double *d_y, size_t total, int *d_err, double timeout_s);
 
+/* FP64 pipe probe: sustained DFMA/s of the device (8 independent chains per thread), for the FP64 cross-check of the
+ * HBM roofline; synchronises */
+int b200_fp64_probe(double *dfma_per_second);
+
 /* Host-resident L-vectors (-memtype host; CeedVectorSetArray(HOST) ... TakeArray(HOST), matops.c:40-50): the fused
  * apply as a pipeline  H2D of x chunks | kernel on element chunks | D2H of finished y rows  on three streams.
  * chunk_end[c] = one past the last element of chunk c (multiples of b200_elems_per_block(Q) except the last);
