@@ -385,8 +385,15 @@ int b200_apply_hostpipe(int jacobian, int problem, const b200_physics *phys, int
   enum { MAXC = 64 };
   static cudaStream_t s_in = nullptr, s_out = nullptr;
   static cudaEvent_t ev_in[MAXC], ev_k[MAXC], ev_start;
+  static int pipe_device = -1;
   if (nchunks < 1 || nchunks > MAXC) return b200::set_error_msg("b200_apply_hostpipe: chunk count out of range");
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (s_in && dev != pipe_device)
+    return b200::set_error_msg("b200_apply_hostpipe: the process changed its CUDA device after the first host-vector apply "
+                               "(one process per GPU is the supported model)");
   if (!s_in) {
+    pipe_device = dev;
     B200_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     B200_CHECK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     for (int i = 0; i < MAXC; i++) {
