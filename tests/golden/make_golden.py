@@ -55,6 +55,11 @@ def run(which, Q, J, w, ug, dug, nu=0.3, E=1.0):
         f, gradu = oracle.call_qf(name + "F", which, phys, Q, [ug.reshape(9, Q), qd], [9, 9])
         (df,) = oracle.call_qf(name + "dF", which, phys, Q, [dug.reshape(9, Q), qd, gradu], [9])
         out[name + "F"], out[name + "F_gradu"], out[name + "dF"] = f, gradu, df
+    # one-shot post-processing QFunctions (setuplibceed.c:645-737): strain energy, nodal diagnostics
+    upt = np.ascontiguousarray(J.reshape(9, Q)[3:6] - 0.1)   # any numbers: the displacement passes through
+    for name in ("LinElas", "HyperSS", "HyperFS"):
+        (out[name + "Energy"],) = oracle.call_qf(name + "Energy", which, phys, Q, [ug.reshape(9, Q), qd], [1])
+        (out[name + "Diagnostic"],) = oracle.call_qf(name + "Diagnostic", which, phys, Q, [upt, ug.reshape(9, Q), qd], [8])
     # forcing / manufactured solution: coordinates = the first three rows of J (any numbers will do)
     xyz = J.reshape(9, Q)[:3] + 0.25
     (out["SetupMMSForce"],) = oracle.call_qf("SetupMMSForce", which, phys, Q, [xyz, qd], [3])

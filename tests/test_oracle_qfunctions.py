@@ -13,7 +13,8 @@ from oracle import oracle  # noqa: E402
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "qf_golden.npz"))
 NAMES = ["qdata", "LinElasF", "LinElasdF", "HyperSSF", "HyperSSF_gradu", "HyperSSdF",
-         "HyperFSF", "HyperFSF_gradu", "HyperFSdF", "SetupMMSForce", "MMSTrueSoln", "SetupConstantForce"]
+         "HyperFSF", "HyperFSF_gradu", "HyperFSdF", "SetupMMSForce", "MMSTrueSoln", "SetupConstantForce",
+         "LinElasEnergy", "LinElasDiagnostic", "HyperSSEnergy", "HyperSSDiagnostic", "HyperFSEnergy", "HyperFSDiagnostic"]
 
 # SURVEY.md Appendix F (reference headers, gcc -O2): values at q = 1 unless noted
 APPF = {
