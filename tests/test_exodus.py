@@ -163,3 +163,17 @@ def test_ell_coarse_matrix_from_element_matrices_on_cpu():
     sm.diagonal(D)
     assert np.allclose(D.numpy(), np.diag(A)[dm._fo_host], rtol=0, atol=1e-12)
     assert sm.nslots <= 81 and sm.nslots >= 27 * 3 // 3
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/meshes/Tube8_32e_2ss_us.exo"), reason="/root/reference not mounted")
+def test_reference_tube_mesh_solves_with_its_side_sets_clamped():
+    """README.rst:63 style run (`-mesh Tube8_... -bc_clamp 998,999 -bc_clamp_999_translate ...`) on the oracle operators"""
+    from oracle_levels import oracle_solve
+    m = HexMesh.from_file("/root/reference/meshes/Tube8_32e_2ss_us.exo")
+    ext = float(np.ptp(m.vertices, axis=0).max())
+    app = AppCtx(problem="hyperFS", degree=2, num_steps=2, mesh=m, nu=0.3, E=1e6,
+                 clamp={998: [0, 0, 0, 0, 0, 1, 0], 999: [0, -0.02 * ext, 0.03 * ext, 0, 0, 1, 0]})
+    out, U = oracle_solve(app)
+    assert out["converged"] and out["snes_its"] <= 8
+    # the clamped end moved by the prescribed translation, the fixed end did not: check through the residual's state
+    assert float(U.abs().max()) > 0.02 * ext
