@@ -5,14 +5,17 @@ import torch
 
 from ceedpetscsolid_b200 import matops, setuplibceed, solver
 from ceedpetscsolid_b200.elasticity import Elasticity
-from ceedpetscsolid_b200.mesh import BoxMesh
+from ceedpetscsolid_b200.mesh import BoxMesh, grid_for
 from oracle import oracle
 
 
 class OracleShared:
-    def __init__(self, app, masked=False):
+    def __init__(self, app, masked=False, dist=None, rank=0, world=1):
         self.app, self.masked = app, masked
-        self.mesh = app.mesh if getattr(app, "mesh", None) is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
+        self.dist, self.rank, self.world = dist, rank, world
+        self.gmesh = app.mesh if getattr(app, "mesh", None) is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
+        self.grid = grid_for(world)
+        self.mesh = self.gmesh.brick(self.grid, rank) if world > 1 else self.gmesh
         self.degrees = setuplibceed.level_degrees(app.degree, app.multigrid)
         p = app.degree
         self.Q = p + 1 + app.qextra
@@ -30,7 +33,12 @@ class OracleLevel:
         self.P = self.deg + 1
         self.B, self.D, _, _ = oracle.basis_1d(self.P, sh.Q, 0)
         self.off = mesh.offsets(self.deg)
-        self.dm = matops.LevelDM(mesh, self.deg, bc_faces=list(app.clamp.keys()), device="cpu", masked=sh.masked)
+        halo = None
+        if sh.world > 1:
+            from ceedpetscsolid_b200.halo import Halo
+            halo = Halo(sh.gmesh, sh.grid, sh.rank, self.deg, sh.dist, device="cpu")
+        self.dm = matops.LevelDM(mesh, self.deg, bc_faces=list(app.clamp.keys()), halo=halo, device="cpu", masked=sh.masked,
+                                 shared=True)
         self.n, self.device = self.dm.nglobal, self.dm.device
         self.Xloc, self.Yloc = self.dm.create_local_vector(matops.MEM_HOST), self.dm.create_local_vector(matops.MEM_HOST)
         self.bc_values = Elasticity._bc_values_fn(self.dm, app) if is_fine else None
@@ -73,8 +81,10 @@ class OracleTransfer:
     def __init__(self, sh, lc, lf):
         self.sh, self.c, self.f = sh, lc, lf
         mesh = sh.mesh
-        mult = oracle.multiplicity(mesh.nelem, lf.P ** 3, 3, lf.dm.lsize, lf.off)
-        self.minv = torch.from_numpy(1.0 / mult)
+        mult = torch.from_numpy(oracle.multiplicity(mesh.nelem, lf.P ** 3, 3, lf.dm.lsize, lf.off))
+        if lf.dm.halo is not None:          # multiplicity summed over ranks (misc.c:115-143)
+            lf.dm.halo.sum_and_share(mult)
+        self.minv = 1.0 / mult
         self.fl, self.cl = lf.dm.create_local_vector(matops.MEM_HOST), lc.dm.create_local_vector(matops.MEM_HOST)
 
     def prolong(self, Xc, Yf):
@@ -92,19 +102,22 @@ class OracleTransfer:
         self.c.dm.local_to_global(torch.from_numpy(y), Yc)
 
 
-def oracle_solve(app, log=None, coarse="hmg", masked=True, **kw):
+def oracle_solve(app, log=None, coarse="hmg", masked=True, dist=None, rank=0, world=1, **kw):
+    """dist/rank/world: brick-partitioned run over torch.distributed (gloo in the CPU tests)"""
     from ceedpetscsolid_b200.elasticity import build_h_dms
-    sh = OracleShared(app, masked)
+    sh = OracleShared(app, masked, dist, rank, world)
     L = len(sh.degrees)
     levels = [OracleLevel(sh, l, l == L - 1) for l in range(L)]
     transfers = [None] + [OracleTransfer(sh, levels[l - 1], levels[l]) for l in range(1, L)]
-    V = solver.Vec(None)
+    V = solver.Vec(dist if world > 1 else None)
     V.consistent = {}
     faces = "all" if app.test_mode else list(app.clamp.keys())
-    h_dms = build_h_dms(sh.mesh, (1, 1, 1), 0, 1, faces, "cpu", masked=masked) \
-        if coarse == "hmg" and getattr(sh.mesh, "structured", True) else None
-    if masked:
-        for dm in [lev.dm for lev in levels] + list(h_dms or []):
+    h_dms = build_h_dms(sh.gmesh, sh.grid, rank, world, faces, "cpu", dist, masked=masked) \
+        if coarse == "hmg" and getattr(sh.gmesh, "structured", True) else None
+    for dm in [lev.dm for lev in levels] + list(h_dms or []):
+        if dm.dot_weight is not None:
+            V.weights[dm.nglobal] = dm.dot_weight
+        if dm.dot_weight is not None or dm.masked:
             V.consistent[dm.nglobal] = dm.make_consistent
     pc = solver.PMultigrid(V, levels, transfers, h_dms=h_dms)
     U = levels[-1].dm.create_global_vector(matops.MEM_HOST)
