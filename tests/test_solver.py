@@ -182,3 +182,53 @@ def test_coo_to_stencil_map_and_stencil_matvec_on_cpu():
     D = torch.zeros(dm.nglobal, dtype=torch.float64)
     m_coo.diagonal(D)
     assert np.allclose(D.numpy(), np.diag(A)[free], rtol=0, atol=1e-12)
+
+
+def test_h_multigrid_coarse_solve_is_mesh_independent_on_the_oracle_operator():
+    """GAMG stand-in: one V(2,2) cycle of the geometric h-multigrid on the assembled p = 1 linear-elasticity matrix
+    (oracle operator, clamped face) as CG preconditioner: the iteration count must not grow with the mesh, unlike Jacobi."""
+    from ceedpetscsolid_b200 import matops
+    from ceedpetscsolid_b200.elasticity import build_h_dms
+    from ceedpetscsolid_b200.mesh import BoxMesh
+    from helpers import PHYS
+    from oracle import oracle
+    its = {}
+    for n in (4, 8):
+        mesh = BoxMesh(n=(n, n, n), perturb=0.05, seed=0)
+        dm = matops.LevelDM(mesh, 1, bc_faces=[(2, 0)], device="cpu", masked=True)
+        B, D, _, _ = oracle.basis_1d(2, 2, 0)
+        qdata = oracle.setup_geo(mesh.nelem, 2, mesh.offsets(1), mesh.coord_lvector())
+        off = mesh.offsets(1)
+
+        def local_apply(x, y):
+            y.copy_(torch.from_numpy(oracle.operator_apply("linElas", True, PHYS, mesh.nelem, 2, 2, B, D, off, qdata, None,
+                                                           x.numpy())))
+
+        V = solver.Vec()
+        V.consistent = {}
+        A = solver.ColoredCoarseMatrix(dm, local_apply)
+        A.assemble()
+        h_dms = build_h_dms(mesh, (1, 1, 1), 0, 1, [(2, 0)], "cpu", masked=True)
+        assert len(h_dms) == (1 if n == 4 else 2)
+        for d in [dm] + h_dms:
+            V.consistent[d.nglobal] = d.make_consistent
+        hmg = solver.HMultigrid(V, A, [dm] + h_dms)
+        hmg.setup()
+        b = torch.from_numpy(np.random.default_rng(n).standard_normal(dm.nglobal))
+        dm.zero_constrained(b)
+        x = torch.zeros_like(b)
+        M = lambda r, z: hmg.solve(r, z)
+        k_mg, reason, _ = solver.pcg(V, A.mult, b, x, M=M, rtol=1e-8, maxit=200)
+        assert reason == "rtol"
+        r = torch.zeros_like(b)
+        A.mult(x, r)
+        assert torch.linalg.norm(r - b) < 1e-6 * torch.linalg.norm(b)
+        D_ = torch.zeros_like(b)
+        A.diagonal(D_)
+        dinv = 1.0 / D_
+        x.zero_()
+        k_jac, _, _ = solver.pcg(V, A.mult, b, x, M=lambda r, z: torch.mul(dinv, r, out=z), rtol=1e-8, maxit=500)
+        its[n] = (k_mg, k_jac)
+    assert its[8][0] <= its[4][0] + 4, its          # multigrid: flat
+    assert its[8][1] >= 1.5 * its[4][1], its        # Jacobi: grows like 1/h
+    assert its[8][0] < its[8][1] / 3, its
