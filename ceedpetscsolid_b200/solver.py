@@ -508,10 +508,13 @@ class SparseCoarseMatrix:
             self.vals.zero_()
             self.vals.index_add_(0, self.dest, self.coo.values())
             return
-        n = self.dm.lsize
-        A = torch.zeros((n, n), dtype=torch.float64)
-        e = torch.zeros(n, dtype=torch.float64)
-        y = torch.zeros(n, dtype=torch.float64)
+        n, dev = self.dm.lsize, self.dm.device
+        if n > 20000:
+            raise RuntimeError("SparseCoarseMatrix: probing the operator column by column is for small test meshes; "
+                               "use the CeedOperatorLinearAssemble path (assemble='coo')")
+        A = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        e = torch.zeros(n, dtype=torch.float64, device=dev)
+        y = torch.zeros(n, dtype=torch.float64, device=dev)
         for j in range(n):
             e.zero_()
             e[j] = 1.0
