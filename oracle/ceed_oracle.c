@@ -494,3 +494,15 @@ int oracle_num_threads(void) {
   return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the benchmark's CPU legs set the
+ * thread count explicitly (all host cores on rank 0) instead of inheriting that. */
+int oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}

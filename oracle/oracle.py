@@ -16,6 +16,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _REF = None
+_NATIVE = None
+_REF_FAST = None
 
 QFN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_double)),
                   C.POINTER(C.POINTER(C.c_double)))
@@ -53,6 +55,19 @@ def lib():
     return _LIB
 
 
+def native_lib():
+    """TIMING build (-O3 -march=native, FP contraction on), compiled on the box that runs it: bench.py's CPU legs only.
+    Parity checks always go through lib()."""
+    global _NATIVE
+    if _NATIVE is None:
+        so = os.path.join(HERE, "_native", "liboracle_native.so")
+        srcs = [os.path.join(HERE, f) for f in ("ceed_oracle.c", "qf_port.c", "Makefile")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["make", "-s", "-C", HERE, "timing"], check=True, stdout=subprocess.DEVNULL)
+        _NATIVE = C.CDLL(so)
+    return _NATIVE
+
+
 def have_ref():
     return os.path.exists(os.path.join(HERE, "_ref", "libref_qf.so"))
 
@@ -65,10 +80,26 @@ def ref():
     return _REF
 
 
+def have_ref_fast():
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_qf_fast.so"))
+
+
+def ref_fast():
+    """The reference's QFunctions at -O3 -march=x86-64-v3 (timing legs only)."""
+    global _REF_FAST
+    if _REF_FAST is None:
+        _REF_FAST = C.CDLL(os.path.join(HERE, "_ref", "libref_qf_fast.so"))
+    return _REF_FAST
+
+
 def qf(name, which="port"):
-    """Function pointer (as c_void_p-castable) of a QFunction; which in {port, ref}."""
+    """Function pointer (as c_void_p-castable) of a QFunction; which in {port, ref, ref_fast, port_native}."""
     if which == "ref":
         return C.cast(getattr(ref(), "ref_" + name), C.c_void_p)
+    if which == "ref_fast":
+        return C.cast(getattr(ref_fast(), "ref_" + name), C.c_void_p)
+    if which == "port_native":
+        return C.cast(getattr(native_lib(), "port_" + name), C.c_void_p)
     return C.cast(getattr(lib(), "port_" + name), C.c_void_p)
 
 
@@ -146,9 +177,11 @@ def setup_geo(nelem, Q, xoffsets, xcoord, which=None):
 
 
 def operator_apply(problem, jacobian, phys, nelem, P, Q, B, D, offsets, qdata, gradu, x,
-                   which=None, y=None):
-    """y = A_loc x (zeroed first, CeedOperatorApply semantics).  Residual writes gradu."""
+                   which=None, y=None, native=False):
+    """y = A_loc x (zeroed first, CeedOperatorApply semantics).  Residual writes gradu.
+    native=True runs the -march=native timing build of the operator loop (bench.py CPU legs)."""
     which = which or default_which()
+    L = native_lib() if native else lib()
     fname, dfname, has_gradu = PROBLEMS[problem]
     mode = 0 if not has_gradu else (2 if jacobian else 1)
     x = _f64(x)
@@ -157,7 +190,7 @@ def operator_apply(problem, jacobian, phys, nelem, P, Q, B, D, offsets, qdata, g
     else:
         y[...] = 0
     ctx = Physics(*phys)
-    rc = lib().oracle_operator_apply_add(
+    rc = L.oracle_operator_apply_add(
         qf(dfname if jacobian else fname, which), C.byref(ctx), mode, nelem, P, Q, _p(_f64(B)),
         _p(_f64(D)), _p(_i32(offsets)), _p(qdata), _p(gradu) if has_gradu else None, _p(x), _p(y))
     assert rc == 0
@@ -191,5 +224,10 @@ def transfer(transpose, nelem, Pc, Pf, offc, offf, vin, lsize_out):
     return out
 
 
-def num_threads():
-    return lib().oracle_num_threads()
+def num_threads(native=False):
+    return (native_lib() if native else lib()).oracle_num_threads()
+
+
+def set_num_threads(n, native=False):
+    """OpenMP threads of the oracle's element loops (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    return (native_lib() if native else lib()).oracle_set_num_threads(int(n))

@@ -1,0 +1,50 @@
+"""Oracle parity AT THE BASELINE.json CONFIG SIZES (SURVEY.md 8(a) shorthands):
+
+  C2  hyperSS degree 3, box 32^3  ( 32 768 elements,  2.7 M L-dofs)
+  C3  hyperFS degree 4, box 64^3  (262 144 elements, 50.9 M L-dofs)
+
+Full-vector comparison of the residual (+ the gradu it stores), the Jacobian on EVERY p-multigrid
+level and the operator diagonal on every level, /gpu/b200 through the libCEED C API vs the CPU
+oracle (restated /cpu/self executing the reference's own QFunctions), rel <= 1e-12 (north_star).
+The oracle's element loops run on all host threads (the scatter stays serial, as /cpu/self).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import PHYS, OracleProblem, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("problem,n,p", [("hyperSS", 32, 3), ("hyperFS", 64, 4)], ids=["C2", "C3"])
+def test_full_size_residual_jacobian_diagonal_match_the_oracle(problem, n, p):
+    import gpu_helpers as G
+    from oracle import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)
+    g = G.GpuProblem(problem, n, p)
+    o = OracleProblem(problem, n, p)
+    assert o.nelem == n ** 3 and g.fine.opApply.is_fused
+    # residual on the fine level + the stored displacement gradient
+    yo = o.residual_fine(o.u_fine)
+    assert rel_err(g.residual(), yo) < TOL
+    gu = g.strided_to_plain(g.fine.ErestrictGradui, g.fine.gradu)
+    assert rel_err(gu, o.gradu) < TOL
+    del gu, yo
+    # Jacobian + diagonal on every level (all levels integrate on the fine quadrature data)
+    rng = np.random.default_rng(1)
+    for level, deg in enumerate(g.degrees):
+        P = deg + 1
+        B, D, _, _ = oracle.basis_1d(P, o.Q, 0)
+        off = o.mesh.offsets(deg)
+        lsize = o.mesh.lsize(deg)
+        x = rng.standard_normal(lsize)
+        yo = oracle.operator_apply(problem, True, PHYS, o.nelem, P, o.Q, B, D, off, o.qdata, o.gradu, x)
+        assert g.data[level].opJacob.is_fused
+        e_j = rel_err(g.jacobian(level, x), yo)
+        do = oracle.operator_diagonal(problem, PHYS, o.nelem, P, o.Q, B, D, off, o.qdata, o.gradu, lsize)
+        e_d = rel_err(g.diagonal(level), do)
+        print(f"{problem} {n}^3 degree {deg}/{p}: Jacobian {e_j:.2e}, diagonal {e_d:.2e}")
+        assert e_j < TOL and e_d < TOL, (level, deg, e_j, e_d)
