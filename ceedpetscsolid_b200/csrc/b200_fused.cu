@@ -24,6 +24,8 @@
 // around the unmodified QFunction.  See DESIGN.md for the roofline arithmetic.
 #include "b200_qf.cuh"
 
+#include <string.h>
+
 namespace b200 {
 
 template <int P, int Q> struct Mats {
@@ -51,6 +53,18 @@ template <int Q> struct Cfg {
 
 #define IDX(c, x, y, z) ((c) * SC + (z) * SZ + (y) * SY + (x))
 
+// Component stride of the fused apply kernels.  The line stages never mix components, so the stride between
+// component lattices is free: for P = Q = 5 a pad of 14 doubles makes the final scatter sweep (lanes run over
+// (node, component) with the component fastest) bank-conflict free as well (97 wavefronts per CTA where 94 is
+// ideal, 188 unpadded; tools/smem_pad.py, checked in tests/test_abi_and_layout.py).  No pad helps the other pairs.
+__host__ __device__ constexpr int odd_extent(int Q) { return (Q % 2) ? Q : Q + 1; }
+__host__ __device__ constexpr int apply_sc(int P, int Q) {
+  return odd_extent(Q) * odd_extent(Q) * odd_extent(Q) + ((P == 5 && Q == 5) ? 14 : 0);
+}
+__host__ __device__ constexpr int apply_se(int Q, int SC) {
+  return elems_per_block(Q) == 16 ? ((9 * SC) | 1) : 9 * SC + ((16 / elems_per_block(Q) - (9 * SC) % 16) + 16) % 16;
+}
+
 // one thread asks the L2 to fetch this CTA's whole slab of per-point data (contiguous in the
 // q-blocked layout) while the CTA is busy with the gather and the interpolation stages
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) {
@@ -60,7 +74,10 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) 
 
 enum { MODE_RESIDUAL = 0, MODE_JACOBIAN = 1 };
 
-template <int P, int Q, int PROB, int MODE>
+// FULL: every CTA of the launch owns a complete group of EB elements, so the plane stride of the q-blocked
+// per-point data is a compile-time constant and every stream load is [base + immediate] (the tail group of a
+// launch, if any, runs through the FULL = false instantiation in a second one-CTA launch).
+template <int P, int Q, int PROB, int MODE, bool FULL>
 // min CTAs/SM: 5 x 128 threads caps the Jacobian kernels at 96 registers (no spills at P=Q=5) and
 // measured 3.5 % faster than 4 x 128 regs; the residual kernels keep all registers
 // (residual kernels: 4 CTAs/SM (128 registers, a few spilled words) measured 20 % faster than 1-2 CTAs at 228 registers)
@@ -68,36 +85,41 @@ __global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::N
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y,
-              const unsigned *__restrict__ scat_tab) {
-  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
-  constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
+              const unsigned *__restrict__ scat_tab, int offsets_ahead) {
+  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, P3 = P * P * P;
+  constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = apply_sc(P, Q), SE = apply_se(Q, SC);
   constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10;
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
   const int blk = blockIdx.x;
   const int rem = nelem - blk * EB;
-  const int ebn = rem < EB ? rem : EB;
-  const bool act = t < T && eb < ebn;
+  const int ebn = FULL ? EB : (rem < EB ? rem : EB);
+  const bool act = t < T && (FULL || eb < ebn);
   const int e = blk * EB + eb;
   double *R0 = smem + eb * SE, *R1 = R0 + 3 * SC, *R2 = R1 + 3 * SC;
-  // per-point data of this CTA: slab base, lane offset and plane stride (q-blocked layout)
-  const double *qslab = qa + (size_t)blk * EB * NC * Q3;
-  const size_t ebt = (size_t)ebn * T;
-  const int lane = t * ebn + eb;
-  if (tid == 0) l2_prefetch_bulk(qslab, (unsigned)(ebt * Q * NC * sizeof(double)));
+  // per-point data of this CTA: slab base + lane offset, plane stride (q-blocked layout)
+  const size_t ebt = FULL ? (size_t)(EB * T) : (size_t)ebn * T;
+  const double *qlane = qa + (size_t)blk * EB * NC * Q3 + (FULL ? tid : t * ebn + eb);
+  if (tid == 0) l2_prefetch_bulk(qa + (size_t)blk * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
+  // ... and the element offsets of a CTA that starts about one wave of resident CTAs later: its gather then
+  // begins with an L2 hit instead of a DRAM round trip in front of the dependent loads of x
+  if (FULL && tid == 32 && offsets_ahead > 0 && (long long)(blk + offsets_ahead + 1) * EB <= nelem)
+    l2_prefetch_bulk(offsets + (size_t)(blk + offsets_ahead) * EB * P3, (unsigned)(EB * P3 * sizeof(int)));
 
   int *soff = reinterpret_cast<int *>(smem + EB * SE);
   // ---- phase 0: gather node z-lines, contract z with B
   if (act && a < P && b < P) {
     double r[3][P];
     const int *off = offsets + (size_t)e * P3 + b * P + a;
+    int o[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) o[k] = __ldg(off + k * P * P);
 #pragma unroll
     for (int k = 0; k < P; k++) {
-      const int o = __ldg(off + k * P * P);
-      soff[eb * P3 + (k * P + b) * P + a] = o;  // parked for the scatter at the end
+      soff[eb * P3 + (k * P + b) * P + a] = o[k];  // parked for the scatter at the end
 #pragma unroll
-      for (int c = 0; c < 3; c++) r[c][k] = __ldg(x + o + c);
+      for (int c = 0; c < 3; c++) r[c][k] = __ldg(x + o[k] + c);
     }
 #pragma unroll
     for (int c = 0; c < 3; c++)
@@ -157,7 +179,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   double qn[NC];  // per-point data of the NEXT quadrature point: loads stay in flight under the math
   if (act) {
 #pragma unroll
-    for (int n = 0; n < NC; n++) qn[n] = __ldcs(qslab + (size_t)(n * Q) * ebt + lane);
+    for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q) * ebt);
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       double in[Q];
@@ -192,7 +214,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
       for (int n = 0; n < NC; n++) qd[n] = qn[n];
       if (qx + 1 < Q) {
 #pragma unroll
-        for (int n = 0; n < NC; n++) qn[n] = __ldcs(qslab + (size_t)(n * Q + qx + 1) * ebt + lane);
+        for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q + qx + 1) * ebt);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -213,7 +235,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
         } else {
           if (PROB == B200_PROB_HYPERSS) hyperss_f_point(mt, qd[0], A, H, g, W);
           else hyperfs_f_point(mt, qd[0], A, H, g, W);
-          double *gslab = gradu + (size_t)blk * EB * 9 * Q3 + lane;
+          double *gslab = gradu + (size_t)blk * EB * 9 * Q3 + (FULL ? tid : t * ebn + eb);
 #pragma unroll
           for (int c = 0; c < 3; c++)
 #pragma unroll
@@ -317,16 +339,23 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   // consecutive lanes hit consecutive L-vector entries (interlaced dofs) and one RED request touches few
   // sectors.  The (lattice index, offset index, component) of each f is the same for every CTA: it comes
   // from a small table (L1/L2 resident) instead of ~30 integer instructions of div/mod per entry.
+  // All shared-memory reads of the sweep are issued before the first RED so that none waits behind one.
   {
     constexpr int NT = Cfg<Q>::NT, NIT = (EB * 3 * P3 + NT - 1) / NT;
     const int total = ebn * 3 * P3;
     unsigned u[NIT];
 #pragma unroll
-    for (int it = 0; it < NIT; it++) u[it] = (tid + it * NT < total) ? __ldg(scat_tab + tid + it * NT) : 0u;
+    for (int it = 0; it < NIT; it++) u[it] = (FULL && (it + 1) * NT <= EB * 3 * P3) || (tid + it * NT < total) ? __ldg(scat_tab + tid + it * NT) : 0u;
+    double val[NIT];
+    int dst[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      val[it] = smem[u[it] & 0xFFFFu];
+      dst[it] = soff[(u[it] >> 16) & 0xFFFu] + (int)(u[it] >> 28);
+    }
 #pragma unroll
     for (int it = 0; it < NIT; it++)
-      if (tid + it * NT < total)
-        atomicAdd(y + soff[(u[it] >> 16) & 0xFFFu] + (u[it] >> 28), smem[u[it] & 0xFFFFu]);
+      if ((FULL && (it + 1) * NT <= EB * 3 * P3) || tid + it * NT < total) atomicAdd(y + dst[it], val[it]);
   }
 }
 
@@ -365,22 +394,29 @@ __global__ void k_jcache_build(int nelem, int Q, const double *__restrict__ qdat
 
 // -----------------------------------------------------------------------------------
 // Operator diagonal (CeedOperatorLinearAssembleDiagonal, matops.c:227; App. B.5):
-//   diag_e[c][n] = sum_q sum_{d,d'} G_d[q,n] Aq_c[d'][d] G_d'[q,n],
-//   Aq_c[d'][d] = dW[c][d]/dH[c][d']  (unit inputs through the Jacobian point function)
-// G_d = Kronecker(B or D per axis) so each (d,d') term is a 3-stage sum-factorised
-// contraction with the element-wise products B.B, B.D, D.D.
+//   diag_e[c][n] = sum_q sum_{d,d'} G_d[q,n] A_c[d'][d](q) G_d'[q,n]
+// A_c = symmetric 3x3 point block in closed form (diag_blocks_point), G_d = Kronecker(B or D per axis), so
+// each of the six distinct (d,d') terms is a 3-stage sum-factorised contraction with the element-wise
+// products B.B, B.D, D.D.  Term t (Voigt order 00,11,22,12,02,01; off-diagonal terms count twice):
+//   x-stage: S_t[i]    = sum_qx A_t(qx) Mx[sel_x(t)][qx][i]      (x-line owner, registers)
+//   y-stage: Y_s[j]   += sum_qy S_t(qy) My[sel_y(t)][qy][j]      terms merged by their z selector s
+//   z-stage: acc[k]   += sum_qz Y_s(qz) Mz[s][qz][k]
+// The cache slab of the CTA is read once from HBM (component 0) and twice more through L2.
 // -----------------------------------------------------------------------------------
 template <int P, int Q> struct DiagMats {
   double M[3][Q * P];  // [0] B.B  [1] B.D  [2] D.D   (element-wise, [Q][P])
 };
 
 template <int P, int Q, int PROB>
-__global__ void __launch_bounds__(Cfg<Q>::NT)
+__global__ void __launch_bounds__(Cfg<Q>::NT, 384 / Cfg<Q>::NT)
 k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ Material mt, int nelem,
              const int *__restrict__ offsets, const double *__restrict__ jcp, double *__restrict__ diag) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
   constexpr int NC = JCache<PROB>::N;
+  // selectors of term t = (d,d') per axis: (d == axis) + (d' == axis)
+  constexpr int SELX[6] = {2, 0, 0, 0, 1, 1}, SELY[6] = {0, 2, 0, 1, 0, 1}, SELZ[6] = {0, 0, 2, 1, 1, 0};
+  constexpr int VJ[6] = {0, 1, 2, 1, 0, 0}, VK[6] = {0, 1, 2, 2, 2, 1};
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
@@ -389,103 +425,95 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
   const int ebn = rem < EB ? rem : EB;
   const bool act = t < T && eb < ebn;
   const int e = blk * EB + eb;
-  double *R0 = smem + eb * SE, *R1 = R0 + 3 * SC;
-  const size_t gb = (size_t)blk * EB * NC * Q3 + (size_t)(t * ebn + eb);
+  double *R = smem + eb * SE;  // 9 single-component lattices: terms 0..5, then the three z-selector sums
+  const double *qlane = jcp + (size_t)blk * EB * NC * Q3 + (size_t)(t * ebn + eb);
   const size_t ebt = (size_t)ebn * T;
 
+#pragma unroll 1
   for (int c = 0; c < 3; c++) {
-    double acc[P];
-#pragma unroll
-    for (int k = 0; k < P; k++) acc[k] = 0;
-    // the per-point data of this x-line is read ONCE per component: all three unit-gradient directions d'
-    // are pushed through the point Jacobian while the cache entry sits in registers
-    double S[3][3][P];  // [d'][d][i]: x-contracted already
-#pragma unroll
-    for (int dp = 0; dp < 3; dp++)
-#pragma unroll
-      for (int d = 0; d < 3; d++)
-#pragma unroll
-        for (int i = 0; i < P; i++) S[dp][d][i] = 0;
     if (act) {
+      double S[6][P];
+#pragma unroll
+      for (int tt = 0; tt < 6; tt++)
+#pragma unroll
+        for (int i = 0; i < P; i++) S[tt][i] = 0;
+      double qn[NC];
+#pragma unroll
+      for (int n = 0; n < NC; n++) qn[n] = __ldg(qlane + (size_t)(n * Q) * ebt);
 #pragma unroll 1
       for (int qx = 0; qx < Q; qx++) {
-        double qd[NC];
+        double qd[NC], M[6], kappa;
 #pragma unroll
-        for (int n = 0; n < NC; n++) qd[n] = __ldg(jcp + gb + (size_t)(n * Q + qx) * ebt);
+        for (int n = 0; n < NC; n++) qd[n] = qn[n];
+        if (qx + 1 < Q) {
 #pragma unroll
-        for (int dp = 0; dp < 3; dp++) {
-          double H[3][3], W[3][3];
+          for (int n = 0; n < NC; n++) qn[n] = __ldg(qlane + (size_t)(n * Q + qx + 1) * ebt);
+        }
+        diag_blocks_point<PROB>(mt, qd, M, kappa);
+        const double k0 = c == 0 ? qd[0] : (c == 1 ? qd[1] : qd[2]);
+        const double k1 = c == 0 ? qd[3] : (c == 1 ? qd[4] : qd[5]);
+        const double k2 = c == 0 ? qd[6] : (c == 1 ? qd[7] : qd[8]);
+        const double kc[3] = {k0, k1, k2};
 #pragma unroll
-          for (int i = 0; i < 3; i++)
+        for (int tt = 0; tt < 6; tt++) {
+          double At = M[tt] + kappa * kc[VJ[tt]] * kc[VK[tt]];
+          if (tt >= 3) At += At;
 #pragma unroll
-            for (int j = 0; j < 3; j++) H[i][j] = (i == c && j == dp) ? 1. : 0.;
-          jacobian_point<PROB>(mt, qd, H, W);
-#pragma unroll
-          for (int d = 0; d < 3; d++) {
-            const double w = c == 0 ? W[0][d] : (c == 1 ? W[1][d] : W[2][d]);
-            const int sel = (d == 0) + (dp == 0);
-#pragma unroll
-            for (int i = 0; i < P; i++) S[dp][d][i] += dm.M[sel][qx * P + i] * w;
-          }
+          for (int i = 0; i < P; i++) S[tt][i] += dm.M[SELX[tt]][qx * P + i] * At;
         }
       }
+#pragma unroll
+      for (int tt = 0; tt < 6; tt++)
+#pragma unroll
+        for (int i = 0; i < P; i++) R[IDX(tt, i, a, b)] = S[tt][i];
     }
+    __syncthreads();
+    // y-lines (a = i < P, b = qz)
+    if (act && a < P) {
+      double Y[3][P];
 #pragma unroll
-    for (int dp = 0; dp < 3; dp++) {  // d' : direction of the unit input
-      // x-lines (a = qy, b = qz): already contracted along x
-      if (act) {
+      for (int s = 0; s < 3; s++)
 #pragma unroll
-        for (int d = 0; d < 3; d++)
+        for (int j = 0; j < P; j++) Y[s][j] = 0;
 #pragma unroll
-          for (int i = 0; i < P; i++) R0[IDX(d, i, a, b)] = S[dp][d][i];
+      for (int tt = 0; tt < 6; tt++) {
+        double in[Q];
+#pragma unroll
+        for (int qy = 0; qy < Q; qy++) in[qy] = R[IDX(tt, a, qy, b)];
+#pragma unroll
+        for (int j = 0; j < P; j++)
+#pragma unroll
+          for (int qy = 0; qy < Q; qy++) Y[SELZ[tt]][j] += dm.M[SELY[tt]][qy * P + j] * in[qy];
       }
-      __syncthreads();
-      // y-lines (a = i < P, b = qz)
-      if (act && a < P) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          const int sel = (d == 1) + (dp == 1);
-          double in[Q];
+      for (int s = 0; s < 3; s++)
 #pragma unroll
-          for (int qy = 0; qy < Q; qy++) in[qy] = R0[IDX(d, a, qy, b)];
-#pragma unroll
-          for (int j = 0; j < P; j++) {
-            double s = 0;
-#pragma unroll
-            for (int qy = 0; qy < Q; qy++) s += dm.M[sel][qy * P + j] * in[qy];
-            R1[IDX(d, a, j, b)] = s;
-          }
-        }
-      }
-      __syncthreads();
-      // z-lines (a = i < P, b = j < P)
-      if (act && a < P && b < P) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-          const int sel = (d == 2) + (dp == 2);
-          double in[Q];
-#pragma unroll
-          for (int qz = 0; qz < Q; qz++) in[qz] = R1[IDX(d, a, b, qz)];
-#pragma unroll
-          for (int k = 0; k < P; k++) {
-            double s = 0;
-#pragma unroll
-            for (int qz = 0; qz < Q; qz++) s += dm.M[sel][qz * P + k] * in[qz];
-            acc[k] += s;
-          }
-        }
-      }
-      // R0 is rewritten only after the next iteration's first barrier-protected stage has
-      // been preceded by this iteration's second barrier; R1 readers (z-lines) must finish
-      // before the next y-line stage writes R1: that stage sits behind the next barrier.
+        for (int j = 0; j < P; j++) R[IDX(6 + s, a, j, b)] = Y[s][j];
     }
+    __syncthreads();
+    // z-lines (a = i < P, b = j < P)
     if (act && a < P && b < P) {
+      double acc[P];
+#pragma unroll
+      for (int k = 0; k < P; k++) acc[k] = 0;
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        double in[Q];
+#pragma unroll
+        for (int qz = 0; qz < Q; qz++) in[qz] = R[IDX(6 + s, a, b, qz)];
+#pragma unroll
+        for (int k = 0; k < P; k++)
+#pragma unroll
+          for (int qz = 0; qz < Q; qz++) acc[k] += dm.M[s][qz * P + k] * in[qz];
+      }
 #pragma unroll
       for (int k = 0; k < P; k++) {
         const int o = __ldg(offsets + (size_t)e * P3 + (k * P + b) * P + a);
         atomicAdd(diag + o + c, acc[k]);
       }
     }
+    // the next component's x-stage writes lattices 0..5 (their readers passed the second barrier) and its
+    // y-stage writes 6..8 only behind the next barrier, which no thread reaches before finishing this z-stage
   }
 }
 
@@ -639,36 +667,83 @@ template <typename K> static int opt_in_smem(K kern, size_t bytes) {
   return 0;
 }
 
+// per-device one-time state of a kernel instantiation (opt-in shared memory size, small device tables):
+// one process may drive several devices (CeedInit "/gpu/b200:device_id=N")
+constexpr int MAX_DEVICES = 64;
+struct PerDevice {
+  bool configured[MAX_DEVICES] = {};
+  void *table[MAX_DEVICES] = {};
+};
+static int current_device(int *dev) {
+  B200_CHECK(cudaGetDevice(dev));
+  if (*dev < 0 || *dev >= MAX_DEVICES) return set_error_msg("device ordinal out of range");
+  return 0;
+}
+
+// the collocated derivative of a basis is computed once per (P, Q) instantiation and reused while the caller
+// keeps passing the same interp1d / grad1d values
+template <int P, int Q> static int cached_mats(const double *hB, const double *hD, Mats<P, Q> &m) {
+  static Mats<P, Q> cache;
+  static double keyB[Q * P], keyD[Q * P];
+  static bool valid = false;
+  if (!valid || memcmp(keyB, hB, sizeof keyB) || memcmp(keyD, hD, sizeof keyD)) {
+    for (int i = 0; i < Q * P; i++) cache.B[i] = hB[i];
+    if (collocated_grad(P, Q, hB, hD, cache.Gc)) {
+      valid = false;
+      return set_error_msg("basis: no collocated gradient with Gc*B = D (rank-deficient interp1d)");
+    }
+    memcpy(keyB, hB, sizeof keyB);
+    memcpy(keyD, hD, sizeof keyD);
+    valid = true;
+  }
+  m = cache;
+  return 0;
+}
+
+// one wave of resident CTAs (5 per SM on 148 SMs), rounded up: how far ahead a CTA prefetches element offsets
+constexpr int OFFSETS_AHEAD = 1024;
+
 template <int P, int Q, int PROB, int MODE>
 static int launch_apply(const Material &mt, int nelem, const double *hB, const double *hD, const int *offsets,
                         const double *qa, double *gradu, const double *x, double *y) {
   Mats<P, Q> m;
-  for (int i = 0; i < Q * P; i++) m.B[i] = hB[i];
-  if (collocated_grad(P, Q, hB, hD, m.Gc)) return set_error_msg("basis: no collocated gradient with Gc*B = D (rank-deficient interp1d)");
-  auto kern = k_fused_apply<P, Q, PROB, MODE>;
-  constexpr int EB = Cfg<Q>::EB, P3 = P * P * P, SC = Cfg<Q>::SC, SZ = Cfg<Q>::SZ, SY = Cfg<Q>::SY;
-  const size_t smem_bytes = Cfg<Q>::SMEM + sizeof(int) * EB * P3;
-  static bool configured = false;
-  static unsigned *d_tab = nullptr;  // per device in principle; one device per process here
-  if (!configured) {
+  if (int rc = cached_mats<P, Q>(hB, hD, m)) return rc;
+  auto kern = k_fused_apply<P, Q, PROB, MODE, true>;
+  auto kern_tail = k_fused_apply<P, Q, PROB, MODE, false>;
+  constexpr int EB = Cfg<Q>::EB, P3 = P * P * P, SZ = Cfg<Q>::SZ, SY = Cfg<Q>::SY, SC = apply_sc(P, Q), SE = apply_se(Q, SC);
+  constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10, Q3 = Q * Q * Q;
+  const size_t smem_bytes = sizeof(double) * EB * SE + sizeof(int) * EB * P3;
+  static PerDevice pd;
+  int dev;
+  if (int rc = current_device(&dev)) return rc;
+  if (!pd.configured[dev]) {
     if (int rc = opt_in_smem(kern, smem_bytes)) return rc;
+    if (int rc = opt_in_smem(kern_tail, smem_bytes)) return rc;
     // scatter table: f = (el, node, c) with c fastest -> lattice index | offset index << 16 | c << 28
-    static_assert(EB * Cfg<Q>::SE < 65536 && EB * P3 < 4096, "scatter table packing");
+    static_assert(EB * SE < 65536 && EB * P3 < 4096, "scatter table packing");
     unsigned h[EB * P3 * 3];
     for (int el = 0; el < EB; el++)
       for (int node = 0; node < P3; node++)
         for (int c = 0; c < 3; c++) {
           const int i = node % P, j = (node / P) % P, k = node / (P * P);
-          h[(el * P3 + node) * 3 + c] = (unsigned)(el * Cfg<Q>::SE + IDX(c, i, j, k)) | ((unsigned)(el * P3 + node) << 16) | ((unsigned)c << 28);
+          h[(el * P3 + node) * 3 + c] = (unsigned)(el * SE + IDX(c, i, j, k)) | ((unsigned)(el * P3 + node) << 16) | ((unsigned)c << 28);
         }
-    B200_CHECK(cudaMalloc(&d_tab, sizeof h));
-    B200_CHECK(cudaMemcpy(d_tab, h, sizeof h, cudaMemcpyHostToDevice));
-    configured = true;
+    B200_CHECK(cudaMalloc(&pd.table[dev], sizeof h));
+    B200_CHECK(cudaMemcpy(pd.table[dev], h, sizeof h, cudaMemcpyHostToDevice));
+    pd.configured[dev] = true;
   }
-  const int nblk = (nelem + EB - 1) / EB;
-  if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y, d_tab);
-  B200_LAUNCH_CHECK("k_fused_apply");
+  const unsigned *d_tab = static_cast<const unsigned *>(pd.table[dev]);
+  const int nfull = nelem / EB, ntail = nelem - nfull * EB;
+  if (nfull) {
+    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, OFFSETS_AHEAD);
+    B200_LAUNCH_CHECK("k_fused_apply");
+  }
+  if (ntail) {  // the partial group at the end of the element range: same kernel with run-time group extent
+    const size_t e0 = (size_t)nfull * EB;
+    kern_tail<<<1, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, ntail, offsets + e0 * P3, qa + e0 * NC * Q3,
+                                                       gradu ? gradu + e0 * 9 * Q3 : nullptr, x, y, d_tab, 0);
+    B200_LAUNCH_CHECK("k_fused_apply(tail)");
+  }
   return 0;
 }
 

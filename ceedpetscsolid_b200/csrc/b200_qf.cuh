@@ -341,18 +341,60 @@ B200_DI void jacobian_point(const Material &mt, const double *jc, const double (
   } else {
     // A holds K' here
     double gt[3][3], Z[3][3], bm[3][3];
-    const double bv[6] = {jc[9], jc[10], jc[11], jc[12], jc[13], jc[14]};
+    // mu folded into b once (6 multiplies) so that every entry of Z is one multiply-or-fma start + 3 fma
+    const double bv[6] = {mt.mu * jc[9], mt.mu * jc[10], mt.mu * jc[11], mt.mu * jc[12], mt.mu * jc[13], mt.mu * jc[14]};
     voigt_sym(bv, bm);
     phys_grad(A, H, gt);  // gt[c][j] = sum_m H[c][m] K'[m][j]
-    const double cw = mt.mu, bw = mt.mu - mt.lambda * jc[15];
+    const double bw = mt.mu - mt.lambda * jc[15];
     const double aw = mt.lambda * (gt[0][0] + gt[1][1] + gt[2][2]);
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
-      for (int j = 0; j < 3; j++)
-        Z[c][j] = cw * (gt[c][0] * bm[0][j] + gt[c][1] * bm[1][j] + gt[c][2] * bm[2][j]) + bw * gt[j][c] +
-                  (c == j ? aw : 0.);
+      for (int j = 0; j < 3; j++) {
+        double z = c == j ? fma(bw, gt[c][c], aw) : bw * gt[j][c];
+        z = fma(gt[c][0], bm[0][j], z);
+        z = fma(gt[c][1], bm[1][j], z);
+        Z[c][j] = fma(gt[c][2], bm[2][j], z);
+      }
     pull_back(A, Z, W);  // W[c][k] = sum_m K'[k][m] Z[c][m]
+  }
+}
+
+// Diagonal point blocks in closed form.  Every Jacobian of this path has the shape
+//     W = [ m1 gt b + k1 gt^T + k2 tr(gt) I ] K^T,   gt = H K      (K = cached geometry, b symmetric)
+// so the 3x3 block of component c, A_c[d'][d] = dW[c][d] / dH[c][d'], is
+//     A_c = m1 K b K^T + (k1 + k2) k_c k_c^T,     k_c[d] = K[d][c]
+// (symmetric; the first term is the same for all three components).  Returns M = m1 K b K^T in Voigt order
+// (00,11,22,12,02,01) and kappa = k1 + k2:
+//   linElas  m1 = c3, b = I, kappa = c1 - c3      (the reference's shear factor, linElas.h:137-139, included)
+//   hyperSS  m1 = mu, b = I, kappa = mu + lambda s
+//   hyperFS  m1 = mu, b = F F^T, kappa = lambda + mu - lambda ln J
+// ~70 FP64 operations per point for all three components, instead of 9 unit inputs through jacobian_point.
+template <int PROB>
+B200_DI void diag_blocks_point(const Material &mt, const double *jc, double (&M)[6], double &kappa) {
+  const int vj[6] = {0, 1, 2, 1, 0, 0}, vk[6] = {0, 1, 2, 2, 2, 1};
+  double Kb[3][3];
+  if (PROB == B200_PROB_HYPERFS) {
+    double bm[3][3];
+    const double bv[6] = {jc[9], jc[10], jc[11], jc[12], jc[13], jc[14]};
+    voigt_sym(bv, bm);
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Kb[d][j] = jc[3 * d] * bm[0][j] + jc[3 * d + 1] * bm[1][j] + jc[3 * d + 2] * bm[2][j];
+    kappa = mt.lambda + mt.mu - mt.lambda * jc[15];
+  } else {
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Kb[d][j] = jc[3 * d + j];
+    kappa = PROB == B200_PROB_HYPERSS ? mt.mu + mt.lambda * jc[9] : mt.le_c1 - mt.le_c3;
+  }
+  const double m1 = PROB == B200_PROB_LINELAS ? mt.le_c3 : mt.mu;
+#pragma unroll
+  for (int t = 0; t < 6; t++) {
+    const int d = vj[t], e = vk[t];
+    M[t] = m1 * (Kb[d][0] * jc[3 * e] + Kb[d][1] * jc[3 * e + 1] + Kb[d][2] * jc[3 * e + 2]);
   }
 }
 

@@ -32,6 +32,7 @@ def hostlib(tmp_path_factory):
     lib = C.CDLL(so)
     lib.qf_host_post.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp]
     lib.qf_host_resjac.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp, dp, dp]
+    lib.qf_host_diagblocks.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp]
     return lib
 
 
@@ -57,6 +58,25 @@ def test_residual_and_cached_jacobian_match_the_reference_qfunctions(hostlib, ta
         assert _rel(gradu, GOLD[f"{tag}_{name}F_gradu"]) < 1e-13
     # the Jacobian goes through the cache (16 / 10 / 9 doubles per point, weight folded into the geometry)
     assert _rel(ddv, GOLD[f"{tag}_{name}dF"]) < 5e-13, name
+
+
+@pytest.mark.parametrize("tag", ["katF", "rnd"])
+@pytest.mark.parametrize("name", list(PROBS))
+def test_closed_form_diagonal_blocks_equal_unit_inputs_through_the_jacobian(hostlib, tag, name):
+    """k_fused_diag builds the 3x3 point blocks dW[c][d]/dH[c][d'] in closed form (diag_blocks_point); the reference's
+    diagonal assembly pushes unit inputs through the Jacobian QFunction.  Same numbers; also with the
+    smoother's material constants (GetDiag_Ceed context swap, matops.c:215-217)."""
+    qd = np.ascontiguousarray(GOLD[f"{tag}_qdata"])
+    Q = qd.shape[1]
+    du = np.ascontiguousarray(GOLD[f"{tag}_ug"].reshape(9, Q))
+    for nu, E in ((0.3, 1.0), (0.45, 2.5)):
+        closed, probed = np.zeros((27, Q)), np.zeros((27, Q))
+        assert hostlib.qf_host_diagblocks(PROBS[name], nu, E, Q, _p(du), _p(qd), _p(closed), _p(probed)) == 0
+        assert np.abs(probed).max() > 0
+        assert _rel(closed, probed) < 1e-13, (name, nu)
+        # symmetric blocks
+        c = closed.reshape(3, 3, 3, Q)
+        assert _rel(c, c.transpose(0, 2, 1, 3)) < 1e-13
 
 
 @pytest.mark.parametrize("name", list(PROBS))
