@@ -106,6 +106,8 @@ _proto("CeedOperatorLinearAssemble", _vp, _vp)
 _proto("CeedOperatorDestroy", _pvp)
 _proto("CeedOperatorIsFusedB200", _vp, C.POINTER(_i))
 _proto("CeedOperatorApplyAddRangeB200", _vp, _vp, _vp, _i, _i)
+_proto("CeedOperatorSetTransferScalingB200", _vp, _vp, _i)
+_proto("CeedIsDeterministic", _vp, _vp)
 _proto("CeedB200LaunchCount", restype=C.c_ulonglong)
 _proto("CeedB200LaunchCountReset", restype=None)
 _proto("CeedB200SetStream", _vp, _vp)
@@ -154,7 +156,7 @@ _proto("b200_vec_reciprocal", _vp, _sz)
 _proto("b200_elems_per_block", _i)
 _proto("b200_fused_supported", _i, _i)
 _proto("b200_jcache_ncomp", _i)
-_proto("b200_apply_transfer", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp)
+_proto("b200_apply_transfer", _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp)
 
 # sentinels are exported data symbols holding pointers
 def _sentinel(name):
@@ -238,6 +240,13 @@ class Ceed(_Obj):
         m = C.c_int()
         lib.CeedGetPreferredMemType(self.h, C.byref(m))
         return m.value
+
+    @property
+    def is_deterministic(self):
+        """CeedIsDeterministic: 1 for "/gpu/b200:deterministic" (ordered, atomic-free transposed restrictions)."""
+        d = C.c_int()
+        lib.CeedIsDeterministic(self.h, C.byref(d))
+        return bool(d.value)
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(lib.CeedB200SetStream(self.h, cuda_stream_ptr))
@@ -439,6 +448,12 @@ class Operator(_Obj):
 
     def apply_add_range(self, u, v, start, stop):
         self._chk(lib.CeedOperatorApplyAddRangeB200(self.h, u.h, v.h, int(start), int(stop)))
+
+    def set_transfer_scaling(self, scale, inject=False):
+        """CeedOperatorSetTransferScalingB200: fused transfer operators apply the fine-side inverse multiplicity
+        themselves (matops.c:149,176); inject: the prolongation stores the interpolant instead of summing copies."""
+        self._scale_keep = scale
+        self._chk(lib.CeedOperatorSetTransferScalingB200(self.h, scale.h if scale is not None else None, int(bool(inject))))
 
     def linear_assemble_diagonal(self, assembled):
         self._chk(lib.CeedOperatorLinearAssembleDiagonal(self.h, assembled.h, REQUEST_IMMEDIATE))

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::N
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y,
-              const unsigned *__restrict__ scat_tab, int offsets_ahead) {
+              const unsigned *__restrict__ scat_tab, int offsets_ahead, double *__restrict__ evec) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, P3 = P * P * P;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = apply_sc(P, Q), SE = apply_se(Q, SC);
   constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10;
@@ -176,10 +176,15 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   }
   __syncthreads();
   // ---- phase 3: y-lines (a = qx, b = qz): d/dy -> R1;  phase 4: z-lines (a = qx, b = qy): d/dz -> R2
-  double qn[NC];  // per-point data of the NEXT quadrature point: loads stay in flight under the math
+  // per-point data of the NEXT quadrature point: loads stay in flight under the math (Jacobian kernels; the
+  // hyperFS residual needs the registers for its point function and loads each point where it is used)
+  constexpr bool AHEAD = !(MODE == MODE_RESIDUAL && PROB == B200_PROB_HYPERFS);
+  double qn[NC];
   if (act) {
+    if (AHEAD) {
 #pragma unroll
-    for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q) * ebt);
+      for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q) * ebt);
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       double in[Q];
@@ -210,11 +215,16 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
 #pragma unroll
     for (int qx = 0; qx < Q; qx++) {
       double qd[NC], H[3][3], W[3][3];
+      if (AHEAD) {
 #pragma unroll
-      for (int n = 0; n < NC; n++) qd[n] = qn[n];
-      if (qx + 1 < Q) {
+        for (int n = 0; n < NC; n++) qd[n] = qn[n];
+        if (qx + 1 < Q) {
 #pragma unroll
-        for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q + qx + 1) * ebt);
+          for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q + qx + 1) * ebt);
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NC; n++) qd[n] = __ldcs(qlane + (size_t)(n * Q + qx) * ebt);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -353,9 +363,16 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
       val[it] = smem[u[it] & 0xFFFFu];
       dst[it] = soff[(u[it] >> 16) & 0xFFFu] + (int)(u[it] >> 28);
     }
+    if (evec) {  // deterministic mode: element outputs [e][node][comp], summed in a fixed order by the caller
+      double *ev = evec + (size_t)blk * EB * 3 * P3;
 #pragma unroll
-    for (int it = 0; it < NIT; it++)
-      if ((FULL && (it + 1) * NT <= EB * 3 * P3) || tid + it * NT < total) atomicAdd(y + dst[it], val[it]);
+      for (int it = 0; it < NIT; it++)
+        if ((FULL && (it + 1) * NT <= EB * 3 * P3) || tid + it * NT < total) ev[tid + it * NT] = val[it];
+    } else {
+#pragma unroll
+      for (int it = 0; it < NIT; it++)
+        if ((FULL && (it + 1) * NT <= EB * 3 * P3) || tid + it * NT < total) atomicAdd(y + dst[it], val[it]);
+    }
   }
 }
 
@@ -410,7 +427,8 @@ template <int P, int Q> struct DiagMats {
 template <int P, int Q, int PROB>
 __global__ void __launch_bounds__(Cfg<Q>::NT, 384 / Cfg<Q>::NT)
 k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ Material mt, int nelem,
-             const int *__restrict__ offsets, const double *__restrict__ jcp, double *__restrict__ diag) {
+             const int *__restrict__ offsets, const double *__restrict__ jcp, double *__restrict__ diag,
+             double *__restrict__ evec) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, SE = Cfg<Q>::SE, P3 = P * P * P;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
   constexpr int NC = JCache<PROB>::N;
@@ -506,10 +524,15 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
 #pragma unroll
           for (int qz = 0; qz < Q; qz++) acc[k] += dm.M[s][qz * P + k] * in[qz];
       }
+      if (evec) {
 #pragma unroll
-      for (int k = 0; k < P; k++) {
-        const int o = __ldg(offsets + (size_t)e * P3 + (k * P + b) * P + a);
-        atomicAdd(diag + o + c, acc[k]);
+        for (int k = 0; k < P; k++) evec[((size_t)e * P3 + (k * P + b) * P + a) * 3 + c] = acc[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < P; k++) {
+          const int o = __ldg(offsets + (size_t)e * P3 + (k * P + b) * P + a);
+          atomicAdd(diag + o + c, acc[k]);
+        }
       }
     }
     // the next component's x-stage writes lattices 0..5 (their readers passed the second barrier) and its
@@ -526,8 +549,8 @@ template <int PC, int PF> struct XferMats { double J[PF * PC]; };
 template <int PC, int PF, int TR>
 __global__ void __launch_bounds__(Cfg<PF>::NT)
 k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__restrict__ offc,
-           const int *__restrict__ offf, const double *__restrict__ mult, const double *__restrict__ in,
-           double *__restrict__ out) {
+           const int *__restrict__ offf, const double *__restrict__ mult, int inject, const double *__restrict__ in,
+           double *__restrict__ out, double *__restrict__ evec) {
   constexpr int Q = PF;  // lattice extent used for smem indexing
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, SE = Cfg<Q>::SE;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
@@ -597,8 +620,13 @@ k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__r
 #pragma unroll
         for (int i = 0; i < NI; i++) s += JM(xx, i) * l[i];
         const int o = __ldg(oout + (b * NO + a) * NO + xx);
+        if (!TR && inject) {  // every element sharing the node stores the same interpolant
+          out[o + c] = s;
+          continue;
+        }
         if (!TR && mult) s *= __ldg(mult + o + c);
-        atomicAdd(out + o + c, s);
+        if (evec) evec[((size_t)e * NO * NO * NO + (b * NO + a) * NO + xx) * 3 + c] = s;
+        else atomicAdd(out + o + c, s);
       }
     }
   }
@@ -705,7 +733,7 @@ constexpr int OFFSETS_AHEAD = 1024;
 
 template <int P, int Q, int PROB, int MODE>
 static int launch_apply(const Material &mt, int nelem, const double *hB, const double *hD, const int *offsets,
-                        const double *qa, double *gradu, const double *x, double *y) {
+                        const double *qa, double *gradu, const double *x, double *y, double *evec) {
   Mats<P, Q> m;
   if (int rc = cached_mats<P, Q>(hB, hD, m)) return rc;
   auto kern = k_fused_apply<P, Q, PROB, MODE, true>;
@@ -735,13 +763,14 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
   const unsigned *d_tab = static_cast<const unsigned *>(pd.table[dev]);
   const int nfull = nelem / EB, ntail = nelem - nfull * EB;
   if (nfull) {
-    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, OFFSETS_AHEAD);
+    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, OFFSETS_AHEAD, evec);
     B200_LAUNCH_CHECK("k_fused_apply");
   }
   if (ntail) {  // the partial group at the end of the element range: same kernel with run-time group extent
     const size_t e0 = (size_t)nfull * EB;
     kern_tail<<<1, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, ntail, offsets + e0 * P3, qa + e0 * NC * Q3,
-                                                       gradu ? gradu + e0 * 9 * Q3 : nullptr, x, y, d_tab, 0);
+                                                       gradu ? gradu + e0 * 9 * Q3 : nullptr, x, y, d_tab, 0,
+                                                       evec ? evec + e0 * 3 * P3 : nullptr);
     B200_LAUNCH_CHECK("k_fused_apply(tail)");
   }
   return 0;
@@ -749,7 +778,7 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
 
 template <int P, int Q, int PROB>
 static int launch_diag(const Material &mt, int nelem, const double *hB, const double *hD, const int *offsets,
-                       const double *jc, double *diag) {
+                       const double *jc, double *diag, double *evec) {
   DiagMats<P, Q> dm;
   for (int i = 0; i < Q * P; i++) {
     dm.M[0][i] = hB[i] * hB[i];
@@ -757,32 +786,36 @@ static int launch_diag(const Material &mt, int nelem, const double *hB, const do
     dm.M[2][i] = hD[i] * hD[i];
   }
   auto kern = k_fused_diag<P, Q, PROB>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice pd;
+  int dev;
+  if (int rc = current_device(&dev)) return rc;
+  if (!pd.configured[dev]) {
     if (int rc = opt_in_smem(kern, Cfg<Q>::SMEM)) return rc;
-    configured = true;
+    pd.configured[dev] = true;
   }
   const int nblk = (nelem + Cfg<Q>::EB - 1) / Cfg<Q>::EB;
   if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<Q>::NT, Cfg<Q>::SMEM, g_stream>>>(dm, mt, nelem, offsets, jc, diag);
+  kern<<<nblk, Cfg<Q>::NT, Cfg<Q>::SMEM, g_stream>>>(dm, mt, nelem, offsets, jc, diag, evec);
   B200_LAUNCH_CHECK("k_fused_diag");
   return 0;
 }
 
 template <int PC, int PF, int TR>
-static int launch_transfer(int nelem, const double *hJ, const int *offc, const int *offf, const double *mult,
-                           const double *in, double *out) {
+static int launch_transfer(int nelem, const double *hJ, const int *offc, const int *offf, const double *mult, int inject,
+                           const double *in, double *out, double *evec) {
   XferMats<PC, PF> m;
   for (int i = 0; i < PF * PC; i++) m.J[i] = hJ[i];
   auto kern = k_transfer<PC, PF, TR>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice pd;
+  int dev;
+  if (int rc = current_device(&dev)) return rc;
+  if (!pd.configured[dev]) {
     if (int rc = opt_in_smem(kern, Cfg<PF>::SMEM)) return rc;
-    configured = true;
+    pd.configured[dev] = true;
   }
   const int nblk = (nelem + Cfg<PF>::EB - 1) / Cfg<PF>::EB;
   if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<PF>::NT, Cfg<PF>::SMEM, g_stream>>>(m, nelem, offc, offf, mult, in, out);
+  kern<<<nblk, Cfg<PF>::NT, Cfg<PF>::SMEM, g_stream>>>(m, nelem, offc, offf, mult, inject, in, out, evec);
   B200_LAUNCH_CHECK("k_transfer");
   return 0;
 }
@@ -794,9 +827,9 @@ static int launch_transfer(int nelem, const double *hJ, const int *offc, const i
 
 template <int PROB, int MODE>
 static int dispatch_apply(int P, int Q, const Material &mt, int nelem, const double *hB, const double *hD,
-                          const int *offsets, const double *qa, double *gradu, const double *x, double *y) {
+                          const int *offsets, const double *qa, double *gradu, const double *x, double *y, double *evec) {
 #define X(p, q) \
-  if (P == p && Q == q) return launch_apply<p, q, PROB, MODE>(mt, nelem, hB, hD, offsets, qa, gradu, x, y);
+  if (P == p && Q == q) return launch_apply<p, q, PROB, MODE>(mt, nelem, hB, hD, offsets, qa, gradu, x, y, evec);
   B200_FOR_PQ(X)
 #undef X
   return set_error_msg("fused apply: (P,Q) not instantiated");
@@ -804,9 +837,9 @@ static int dispatch_apply(int P, int Q, const Material &mt, int nelem, const dou
 
 template <int PROB>
 static int dispatch_diag(int P, int Q, const Material &mt, int nelem, const double *hB, const double *hD,
-                         const int *offsets, const double *jc, double *diag) {
+                         const int *offsets, const double *jc, double *diag, double *evec) {
 #define X(p, q) \
-  if (P == p && Q == q) return launch_diag<p, q, PROB>(mt, nelem, hB, hD, offsets, jc, diag);
+  if (P == p && Q == q) return launch_diag<p, q, PROB>(mt, nelem, hB, hD, offsets, jc, diag, evec);
   B200_FOR_PQ(X)
 #undef X
   return set_error_msg("fused diagonal: (P,Q) not instantiated");
@@ -830,36 +863,36 @@ extern "C" int b200_jcache_ncomp(int problem) {
 
 extern "C" int b200_apply_residual(int problem, const b200_physics *phys, int nelem, int P, int Q,
                                    const double *hB, const double *hD, const int *d_offsets,
-                                   const double *d_qdata, double *d_gradu, const double *d_x, double *d_y) {
+                                   const double *d_qdata, double *d_gradu, const double *d_x, double *d_y, double *d_evec) {
   const Material mt = make_material(phys);
   switch (problem) {
-    case B200_PROB_LINELAS: return dispatch_apply<B200_PROB_LINELAS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y);
-    case B200_PROB_HYPERSS: return dispatch_apply<B200_PROB_HYPERSS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y);
-    case B200_PROB_HYPERFS: return dispatch_apply<B200_PROB_HYPERFS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y);
+    case B200_PROB_LINELAS: return dispatch_apply<B200_PROB_LINELAS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y, d_evec);
+    case B200_PROB_HYPERSS: return dispatch_apply<B200_PROB_HYPERSS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y, d_evec);
+    case B200_PROB_HYPERFS: return dispatch_apply<B200_PROB_HYPERFS, MODE_RESIDUAL>(P, Q, mt, nelem, hB, hD, d_offsets, d_qdata, d_gradu, d_x, d_y, d_evec);
   }
   return set_error_msg("b200_apply_residual: unknown problem");
 }
 
 extern "C" int b200_apply_jacobian(int problem, const b200_physics *phys, int nelem, int P, int Q,
                                    const double *hB, const double *hD, const int *d_offsets,
-                                   const double *d_jcache, const double *d_x, double *d_y) {
+                                   const double *d_jcache, const double *d_x, double *d_y, double *d_evec) {
   const Material mt = make_material(phys);
   switch (problem) {
-    case B200_PROB_LINELAS: return dispatch_apply<B200_PROB_LINELAS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y);
-    case B200_PROB_HYPERSS: return dispatch_apply<B200_PROB_HYPERSS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y);
-    case B200_PROB_HYPERFS: return dispatch_apply<B200_PROB_HYPERFS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y);
+    case B200_PROB_LINELAS: return dispatch_apply<B200_PROB_LINELAS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y, d_evec);
+    case B200_PROB_HYPERSS: return dispatch_apply<B200_PROB_HYPERSS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y, d_evec);
+    case B200_PROB_HYPERFS: return dispatch_apply<B200_PROB_HYPERFS, MODE_JACOBIAN>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, nullptr, d_x, d_y, d_evec);
   }
   return set_error_msg("b200_apply_jacobian: unknown problem");
 }
 
 extern "C" int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P, int Q,
                                    const double *hB, const double *hD, const int *d_offsets,
-                                   const double *d_jcache, double *d_diag) {
+                                   const double *d_jcache, double *d_diag, double *d_evec) {
   const Material mt = make_material(phys);
   switch (problem) {
-    case B200_PROB_LINELAS: return dispatch_diag<B200_PROB_LINELAS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag);
-    case B200_PROB_HYPERSS: return dispatch_diag<B200_PROB_HYPERSS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag);
-    case B200_PROB_HYPERFS: return dispatch_diag<B200_PROB_HYPERFS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag);
+    case B200_PROB_LINELAS: return dispatch_diag<B200_PROB_LINELAS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag, d_evec);
+    case B200_PROB_HYPERSS: return dispatch_diag<B200_PROB_HYPERSS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag, d_evec);
+    case B200_PROB_HYPERFS: return dispatch_diag<B200_PROB_HYPERFS>(P, Q, mt, nelem, hB, hD, d_offsets, d_jcache, d_diag, d_evec);
   }
   return set_error_msg("b200_apply_diagonal: unknown problem");
 }
@@ -883,11 +916,13 @@ extern "C" int b200_jcache_build(int problem, int nelem, int Q, const double *d_
 }
 
 extern "C" int b200_apply_transfer(int transpose, int nelem, int Pc, int Pf, const double *hJ, const int *d_offc,
-                                   const int *d_offf, const double *d_mult, const double *d_in, double *d_out) {
-#define XF(pc, pf)                                                                                      \
-  if (Pc == pc && Pf == pf)                                                                             \
-    return transpose ? launch_transfer<pc, pf, 1>(nelem, hJ, d_offc, d_offf, d_mult, d_in, d_out)       \
-                     : launch_transfer<pc, pf, 0>(nelem, hJ, d_offc, d_offf, d_mult, d_in, d_out);
+                                   const int *d_offf, const double *d_mult, int inject, const double *d_in, double *d_out,
+                                   double *d_evec) {
+  if (inject && (transpose || !d_mult)) return set_error_msg("b200_apply_transfer: inject is the prolongation with multiplicity scaling");
+#define XF(pc, pf)                                                                                                      \
+  if (Pc == pc && Pf == pf)                                                                                             \
+    return transpose ? launch_transfer<pc, pf, 1>(nelem, hJ, d_offc, d_offf, d_mult, 0, d_in, d_out, d_evec)            \
+                     : launch_transfer<pc, pf, 0>(nelem, hJ, d_offc, d_offf, d_mult, inject, d_in, d_out, d_evec);
   XF(2, 3) XF(3, 4) XF(4, 5) XF(3, 5) XF(2, 4) XF(2, 5)
 #undef XF
   return set_error_msg("b200_apply_transfer: (Pc,Pf) not instantiated");

@@ -6,6 +6,9 @@
 // These run once per set-up, not per Krylov iteration; they are written for clarity.
 #include "b200_qf.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace b200 {
 
 #define GRID_STRIDE(i, n) \
@@ -252,9 +255,55 @@ __global__ void k_diag_accumulate(int nelem, int P, int Q, const double *__restr
   }
 }
 
+// ---- ordered transpose of an offsets restriction (deterministic mode) -----------------------------------
+// one thread per L-vector entry that is the offset of some node: its E-vector positions are summed in
+// ascending (element, node) order, exactly the order of the serial /cpu/self scatter; no atomics
+__global__ void k_transpose_gather_add(int lsize, const int *__restrict__ tptr, const int *__restrict__ tidx, int elemsize,
+                                       int ncomp, int compstride, int layout, const double *__restrict__ E,
+                                       double *__restrict__ L) {
+  GRID_STRIDE(o, (size_t)lsize) {
+    const int beg = tptr[o], end = tptr[o + 1];
+    if (beg == end) continue;
+    for (int c = 0; c < ncomp; c++) {
+      double s = L[o + (size_t)c * compstride];
+      for (int j = beg; j < end; j++) {
+        const size_t p = (size_t)tidx[j];
+        const size_t e = p / elemsize, n = p - e * elemsize;
+        s += layout ? E[p * ncomp + c] : E[(e * ncomp + c) * elemsize + n];
+      }
+      L[o + (size_t)c * compstride] = s;
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_transpose_gather_add(int lsize, const int *d_tptr, const int *d_tidx, int elemsize, int ncomp,
+                                         int compstride, int layout, const double *d_evec, double *d_L) {
+  if (lsize <= 0) return 0;
+  k_transpose_gather_add<<<grid_for((size_t)lsize, 256), 256, 0, g_stream>>>(lsize, d_tptr, d_tidx, elemsize, ncomp,
+                                                                            compstride, layout, d_evec, d_L);
+  B200_LAUNCH_CHECK("k_transpose_gather_add");
+  return 0;
+}
+
+extern "C" int b200_transpose_map_build(int lsize, size_t n, const int *h_offsets, int *h_tptr, int *h_tidx) {
+  for (int i = 0; i <= lsize; i++) h_tptr[i] = 0;
+  for (size_t p = 0; p < n; p++) {
+    if (h_offsets[p] < 0 || h_offsets[p] >= lsize) return set_error_msg("b200_transpose_map_build: offset out of range");
+    h_tptr[h_offsets[p] + 1]++;
+  }
+  for (int i = 0; i < lsize; i++) h_tptr[i + 1] += h_tptr[i];
+  // stable fill: positions of one offset end up in ascending order
+  int *cur = (int *)malloc(sizeof(int) * (size_t)(lsize > 0 ? lsize : 1));
+  if (!cur) return set_error_msg("b200_transpose_map_build: out of memory");
+  memcpy(cur, h_tptr, sizeof(int) * (size_t)lsize);
+  for (size_t p = 0; p < n; p++) h_tidx[cur[h_offsets[p]]++] = (int)p;
+  free(cur);
+  return 0;
+}
 
 extern "C" int b200_diag_accumulate(int nelem, int P, int Q, const double *d_interp1d, const double *d_grad1d, int din,
                                     int cin, const double *d_dv, double *d_ediag) {

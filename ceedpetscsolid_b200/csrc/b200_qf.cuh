@@ -157,21 +157,55 @@ B200_DI void fs_common(const Material &mt, const double (&g)[3][3], double (&S)[
   voigt_sym(sv, S);
 }
 
-// residual, hyperFS.h:212-276
+// det(I + s) - 1 of a symmetric s in Voigt order (00,11,22,12,02,01), without cancellation for small s
+// (the reference's computeDetCM1, hyperFS.h:72-80, applied to s = 2E)
+B200_DI double det_sym_m1(const double (&e)[6]) {
+  return e[0] * (e[1] * e[2] - e[3] * e[3]) + e[5] * (e[4] * e[3] - e[5] * e[2]) +
+         e[4] * (e[5] * e[3] - e[4] * e[1]) + e[0] + e[1] + e[2] + e[0] * e[1] + e[0] * e[2] +
+         e[1] * e[2] - e[5] * e[5] - e[4] * e[4] - e[3] * e[3];
+}
+
+// residual, hyperFS.h:212-276, in spatial form.  The reference evaluates S = lambda lnJ C^-1 + 2 mu C^-1 E and
+// P = F S; with C^-1 = F^-1 F^-T this is exactly
+//     P = tau F^-T,   tau = mu (b - I) + lambda lnJ I,   b - I = g + g^T + g g^T
+// (Kirchhoff stress): no C^-1, no Voigt round trip, one reciprocal.  b - I is formed from g directly and
+// lnJ = log1p(det b - 1) / 2 with det b - 1 = det C - 1 from the reference's cancellation-free polynomial and its
+// own series (hyperFS.h:45-80), so small strains keep full relative accuracy as in the reference.
 B200_DI void hyperfs_f_point(const Material &mt, double w, const double (&A)[3][3],
                              const double (&H)[3][3], double (&g)[3][3], double (&W)[3][3]) {
-  double S[3][3], Ci[3][3], llnj, F[3][3], Pk[3][3];
   phys_grad(A, H, g);
-  fs_common(mt, g, S, Ci, llnj);
+  const int vj[6] = {0, 1, 2, 1, 0, 0}, vk[6] = {0, 1, 2, 2, 2, 1};
+  double s[6], tau[3][3];
 #pragma unroll
-  for (int a = 0; a < 3; a++)
+  for (int m = 0; m < 6; m++) {
+    const int j = vj[m], k = vk[m];
+    s[m] = g[j][k] + g[k][j] + g[j][0] * g[k][0] + g[j][1] * g[k][1] + g[j][2] * g[k][2];
+  }
+  const double llnj = mt.lambda * log1p_series_shifted(det_sym_m1(s)) / 2.;
+  const double tv[6] = {mt.mu * s[0] + llnj, mt.mu * s[1] + llnj, mt.mu * s[2] + llnj, mt.mu * s[3], mt.mu * s[4], mt.mu * s[5]};
+  voigt_sym(tv, tau);
+  // F^-T = cof(F) / det F, scaled by w:  Kt[n][k] = w / detF * sum_m cof[n][m] A[k][m];   W = tau Kt
+  const double F00 = g[0][0] + 1., F11 = g[1][1] + 1., F22 = g[2][2] + 1.;
+  double cof[3][3];
+  cof[0][0] = F11 * F22 - g[1][2] * g[2][1];
+  cof[0][1] = g[1][2] * g[2][0] - g[1][0] * F22;
+  cof[0][2] = g[1][0] * g[2][1] - F11 * g[2][0];
+  cof[1][0] = g[0][2] * g[2][1] - g[0][1] * F22;
+  cof[1][1] = F00 * F22 - g[0][2] * g[2][0];
+  cof[1][2] = g[0][1] * g[2][0] - F00 * g[2][1];
+  cof[2][0] = g[0][1] * g[1][2] - g[0][2] * F11;
+  cof[2][1] = g[0][2] * g[1][0] - F00 * g[1][2];
+  cof[2][2] = F00 * F11 - g[0][1] * g[1][0];
+  const double wr = w / (F00 * cof[0][0] + g[0][1] * cof[0][1] + g[0][2] * cof[0][2]);
+  double Kt[3][3];
 #pragma unroll
-    for (int b = 0; b < 3; b++) F[a][b] = g[a][b] + (a == b ? 1. : 0.);
+  for (int n = 0; n < 3; n++)
 #pragma unroll
-  for (int a = 0; a < 3; a++)
+    for (int k = 0; k < 3; k++) Kt[n][k] = wr * (cof[n][0] * A[k][0] + cof[n][1] * A[k][1] + cof[n][2] * A[k][2]);
 #pragma unroll
-    for (int b = 0; b < 3; b++) Pk[a][b] = (F[a][0] * S[0][b] + F[a][1] * S[1][b] + F[a][2] * S[2][b]) * w;
-  pull_back(A, Pk, W);
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) W[c][k] = tau[c][0] * Kt[0][k] + tau[c][1] * Kt[1][k] + tau[c][2] * Kt[2][k];
 }
 
 // Jacobian in the reference's own algebra (hyperFS.h:339-459), used by the generic

@@ -424,9 +424,9 @@ int b200_apply_hostpipe(int jacobian, int problem, const b200_physics *phys, int
     const int ne = chunk_end[c] - e0;
     if (ne > 0) {
       const int rc = jacobian
-          ? b200_apply_jacobian(problem, phys, ne, P, Q, hB, hD, d_offsets + (size_t)e0 * P3, d_qa + (size_t)e0 * nc * Q3, d_x, d_y)
+          ? b200_apply_jacobian(problem, phys, ne, P, Q, hB, hD, d_offsets + (size_t)e0 * P3, d_qa + (size_t)e0 * nc * Q3, d_x, d_y, nullptr)
           : b200_apply_residual(problem, phys, ne, P, Q, hB, hD, d_offsets + (size_t)e0 * P3, d_qa + (size_t)e0 * nc * Q3,
-                                d_gradu ? d_gradu + (size_t)e0 * 9 * Q3 : nullptr, d_x, d_y);
+                                d_gradu ? d_gradu + (size_t)e0 * 9 * Q3 : nullptr, d_x, d_y, nullptr);
       if (rc) return rc;
     }
     B200_CHECK(cudaEventRecord(ev_k[c], g_stream));

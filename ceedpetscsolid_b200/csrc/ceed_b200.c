@@ -42,6 +42,10 @@ struct Ceed_private {
   CeedErrorHandler eh;
   char errmsg[1024];
   JCacheEntry *jcaches;
+  /* "/gpu/b200:deterministic": transposed restrictions sum their E-vector in the serial /cpu/self order */
+  int deterministic;
+  double *det_evec;      /* device scratch E-vector shared by the fused kernels (stream-ordered reuse) */
+  size_t det_evec_bytes;
 };
 
 struct CeedVector_private {
@@ -60,6 +64,7 @@ struct CeedElemRestriction_private {
   int strided, backend_strides, layout_q, offsets_borrowed;
   CeedInt strides[3];
   int *d_offsets;
+  int *d_tptr, *d_tidx;  /* deterministic mode: E-vector positions by offset value (CSR), built on first use */
   /* host-pipeline chunk tables (b200_apply_hostpipe), built on first use; pipe_n = -1: not worth it */
   int pipe_n, pipe_q;
   int pipe_end[B200_PIPE_MAXC];
@@ -111,6 +116,9 @@ struct CeedOperator_private {
   int kind, problem;
   int composite, nsubs;
   CeedOperator subs[MAXF];
+  /* fused transfer operators: optional fine-side pointwise scaling (CeedOperatorSetTransferScalingB200) */
+  CeedVector xfer_scale;
+  int xfer_inject;
   /* generic-path work buffers (device), grown on demand */
   double *ebuf[2 * MAXF], *qbuf[2 * MAXF];
   size_t ebytes[2 * MAXF], qbytes[2 * MAXF];
@@ -206,6 +214,7 @@ int CeedInit(const char *resource, Ceed *ceed) {
   Ceed c = (Ceed)calloc(1, sizeof *c);
   if (!c) return CeedError(NULL, 3, "out of memory");
   snprintf(c->resource, sizeof c->resource, "%s", resource);
+  c->deterministic = strstr(resource, ":deterministic") != NULL;
   c->refcount = 1;
   c->eh = g_default_eh ? g_default_eh : CeedErrorAbort;
   *ceed = c;
@@ -230,13 +239,14 @@ int CeedDestroy(Ceed *ceed) {
   if (!ceed || !*ceed) return 0;
   if (--(*ceed)->refcount > 0) { *ceed = NULL; return 0; }
   jcache_drop_for(*ceed, NULL);
+  if ((*ceed)->det_evec) b200_free((*ceed)->det_evec);
   free(*ceed);
   *ceed = NULL;
   return 0;
 }
 int CeedGetResource(Ceed ceed, const char **resource) { *resource = ceed->resource; return 0; }
 int CeedGetPreferredMemType(Ceed ceed, CeedMemType *type) { (void)ceed; *type = CEED_MEM_DEVICE; return 0; }
-int CeedIsDeterministic(Ceed ceed, int *isDeterministic) { (void)ceed; *isDeterministic = 0; return 0; }
+int CeedIsDeterministic(Ceed ceed, int *isDeterministic) { *isDeterministic = ceed->deterministic; return 0; }
 int CeedB200SetStream(Ceed ceed, void *s) { B2(ceed, b200_set_stream(s)); return 0; }
 int CeedB200Synchronize(Ceed ceed) { B2(ceed, b200_sync()); return 0; }
 unsigned long long CeedB200LaunchCount(void) { return b200_launch_count(); }
@@ -483,7 +493,46 @@ int CeedElemRestrictionCreateVector(CeedElemRestriction rstr, CeedVector *lvec, 
   return 0;
 }
 
+/* deterministic mode: CSR of the E-vector positions p = e*elemsize + n by offset value, ascending p */
+static int rstr_transpose_map(CeedElemRestriction r) {
+  Ceed ceed = r->ceed;
+  if (r->d_tptr) return 0;
+  const size_t n = (size_t)r->nelem * r->elemsize;
+  int *off = (int *)malloc((n ? n : 1) * sizeof(int)), *tptr = (int *)malloc(((size_t)r->lsize + 1) * sizeof(int));
+  int *tidx = (int *)malloc((n ? n : 1) * sizeof(int));
+  if (!off || !tptr || !tidx) { free(off); free(tptr); free(tidx); return CeedError(ceed, 3, "out of memory"); }
+  int rc = b200_memcpy_d2h(off, r->d_offsets, n * sizeof(int));
+  if (!rc) rc = b200_transpose_map_build(r->lsize, n, off, tptr, tidx);
+  if (!rc) rc = b200_malloc((void **)&r->d_tptr, ((size_t)r->lsize + 1) * sizeof(int));
+  if (!rc) rc = b200_malloc((void **)&r->d_tidx, (n ? n : 1) * sizeof(int));
+  if (!rc) rc = b200_memcpy_h2d(r->d_tptr, tptr, ((size_t)r->lsize + 1) * sizeof(int));
+  if (!rc) rc = b200_memcpy_h2d(r->d_tidx, tidx, n * sizeof(int));
+  if (!rc) rc = b200_sync();
+  free(off); free(tptr); free(tidx);
+  if (rc) return CeedError(ceed, rc, "deterministic restriction map: %s", b200_last_error());
+  return 0;
+}
+
+/* L += E^T E-vector in the serial (element, node) order; layout as b200_transpose_gather_add */
+static int rstr_ordered_add(CeedElemRestriction r, int layout, const double *evec, double *L) {
+  CeedChk(rstr_transpose_map(r));
+  B2(r->ceed, b200_transpose_gather_add(r->lsize, r->d_tptr, r->d_tidx, r->elemsize, r->ncomp, r->compstride, layout, evec, L));
+  return 0;
+}
+
+/* the Ceed's scratch E-vector (deterministic mode), at least `bytes` long */
+static int det_scratch(Ceed ceed, size_t bytes, double **p) {
+  if (ceed->det_evec_bytes < bytes) {
+    if (ceed->det_evec) { B2(ceed, b200_sync()); B2(ceed, b200_free(ceed->det_evec)); ceed->det_evec = NULL; ceed->det_evec_bytes = 0; }
+    B2(ceed, b200_malloc((void **)&ceed->det_evec, bytes));
+    ceed->det_evec_bytes = bytes;
+  }
+  *p = ceed->det_evec;
+  return 0;
+}
+
 static int rstr_apply_raw(CeedElemRestriction r, int transpose, const double *in, double *out) {
+  if (transpose && !r->strided && r->ceed->deterministic) return rstr_ordered_add(r, 0, in, out);
   if (r->strided == 1)
     B2(r->ceed, b200_restrict_strided(transpose, r->nelem, r->elemsize, r->ncomp, r->backend_strides ? r->layout_q : 0,
                                       r->strides[0], r->strides[1], r->strides[2], in, out));
@@ -529,6 +578,8 @@ int CeedElemRestrictionDestroy(CeedElemRestriction *rstr) {
   if (r == CEED_ELEMRESTRICTION_NONE) return 0;
   if (--r->refcount > 0) return 0;
   if (r->d_offsets && !r->offsets_borrowed) b200_free(r->d_offsets);
+  if (r->d_tptr) b200_free(r->d_tptr);
+  if (r->d_tidx) b200_free(r->d_tidx);
   Ceed c = r->ceed;
   free(r);
   return CeedDestroy(&c);
@@ -1133,6 +1184,7 @@ static int rstr_pipe_setup(CeedElemRestriction r, int Q) {
 static int op_apply_hostpipe(CeedOperator op, CeedVector in, CeedVector out, int *done) {
   Ceed ceed = op->ceed;
   *done = 0;
+  if (ceed->deterministic) return 0;  /* chunked launches scatter with atomics */
   if (op->kind != OP_FUSED_JACOBIAN && op->kind != OP_FUSED_RESIDUAL) return 0;
   if (!in || !out || in == out || !in->h_valid || in->d_valid || !in->h || !out->h) return 0;
   OpField *u = &op->in[0];
@@ -1174,13 +1226,19 @@ static int op_apply_fused_range(CeedOperator op, CeedVector in, CeedVector out, 
   if (in->length < u->r->lsize || out->length < u->r->lsize)
     return CeedError(ceed, 1, "operator %s: active vectors shorter than the restriction's L-vector size %d", op->qf->name, u->r->lsize);
   const int *off = u->r->d_offsets + (size_t)e0 * P3;
+  double *evec = NULL;
+  if (ceed->deterministic) {
+    if (e0 != 0 || e1 != u->r->nelem)
+      return CeedError(ceed, 1, "deterministic mode: element-range applies are not supported (the ordered sum runs over the whole restriction)");
+    CeedChk(det_scratch(ceed, (size_t)u->r->nelem * 3 * P3 * sizeof(double), &evec));
+  }
   if (op->kind == OP_FUSED_JACOBIAN) {
     const double *jc;
     CeedChk(jcache_get(op, &jc));
     CeedChk(vec_dev_read(in, &x));
     CeedChk(vec_dev_rw(out, &y));
     B2(ceed, b200_apply_jacobian(op->problem, &phys, e1 - e0, P, Q, u->b->interp1d, u->b->grad1d, off,
-                                 jc + (size_t)e0 * b200_jcache_ncomp(op->problem) * Q3, x, y));
+                                 jc + (size_t)e0 * b200_jcache_ncomp(op->problem) * Q3, x, y, evec));
   } else {
     const double *qd;
     double *gu = NULL;
@@ -1194,8 +1252,9 @@ static int op_apply_fused_range(CeedOperator op, CeedVector in, CeedVector out, 
     CeedChk(vec_dev_read(in, &x));
     CeedChk(vec_dev_rw(out, &y));
     B2(ceed, b200_apply_residual(op->problem, &phys, e1 - e0, P, Q, u->b->interp1d, u->b->grad1d, off,
-                                 qd + (size_t)e0 * 10 * Q3, gu, x, y));
+                                 qd + (size_t)e0 * 10 * Q3, gu, x, y, evec));
   }
+  if (evec) CeedChk(rstr_ordered_add(u->r, 1, evec, y));
   return 0;
 }
 
@@ -1215,8 +1274,19 @@ int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedReq
     OpField *c = prolong ? &op->in[0] : &op->out[0], *f = prolong ? &op->out[0] : &op->in[0];
     CeedChk(vec_dev_read(in, &x));
     CeedChk(vec_dev_rw(out, &y));
+    const double *mult = NULL;
+    if (op->xfer_scale) {
+      if (op->xfer_scale->length < f->r->lsize) return CeedError(ceed, 1, "transfer scaling vector shorter than the fine L-vector");
+      CeedChk(vec_dev_read(op->xfer_scale, &mult));
+    }
+    const int inject = prolong && mult && op->xfer_inject;
+    CeedElemRestriction ro = prolong ? f->r : c->r;
+    double *evec = NULL;
+    if (ceed->deterministic && !inject)
+      CeedChk(det_scratch(ceed, (size_t)ro->nelem * ro->elemsize * 3 * sizeof(double), &evec));
     B2(ceed, b200_apply_transfer(!prolong, c->r->nelem, c->b->P, c->b->Q, c->b->interp1d, c->r->d_offsets, f->r->d_offsets,
-                                 NULL, x, y));
+                                 mult, inject, x, y, evec));
+    if (evec) CeedChk(rstr_ordered_add(ro, 1, evec, y));
     return 0;
   }
   return op_apply_fused_range(op, in, out, 0, op->in[0].r->nelem);
@@ -1238,6 +1308,25 @@ int CeedOperatorApplyAddRangeB200(CeedOperator op, CeedVector in, CeedVector out
                      start, stop, nelem, EB);
   if (start == stop) return 0;
   return op_apply_fused_range(op, in, out, start, stop);
+}
+
+/* /gpu/b200 extension for the p-multigrid transfer operators (Prolong_Ceed / Restrict_Ceed, matops.c:115-203): the
+ * reference scales the fine vector by the inverse multiplicity in a separate VecPointwiseMult (:149 after the
+ * prolongation, :176 before the restriction).  With a scaling vector set, the fused transfer kernel applies it on
+ * the fly; inject != 0 additionally lets the prolongation STORE the interpolant at every fine node instead of
+ * summing the element copies and dividing by their number (identical for a continuous coarse field).  Apply then
+ * has overwrite semantics on the nodes it reaches.  scale == NULL restores the plain operator. */
+int CeedOperatorSetTransferScalingB200(CeedOperator op, CeedVector scale, int inject) {
+  Ceed ceed = op->ceed;
+  if (op->composite) return CeedError(ceed, 1, "CeedOperatorSetTransferScalingB200: composite operator");
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  if (op->kind != OP_FUSED_TRANSFER)
+    return CeedError(ceed, 1, "CeedOperatorSetTransferScalingB200: operator %s is not a fused transfer operator", op->qf->name);
+  if (scale) scale->refcount++;
+  if (op->xfer_scale) CeedVectorDestroy(&op->xfer_scale);
+  op->xfer_scale = scale;
+  op->xfer_inject = scale ? inject : 0;
+  return 0;
 }
 
 /* libCEED interface semantics: zero every output (active and passive), then ApplyAdd */
@@ -1280,8 +1369,11 @@ int CeedOperatorLinearAssembleAddDiagonal(CeedOperator op, CeedVector assembled,
   double *d;
   CeedChk(jcache_get(op, &jc));
   CeedChk(vec_dev_rw(assembled, &d));
+  double *evec = NULL;
+  if (ceed->deterministic) CeedChk(det_scratch(ceed, (size_t)u->r->nelem * u->r->elemsize * 3 * sizeof(double), &evec));
   B2(ceed, b200_apply_diagonal(op->problem, &phys, u->r->nelem, u->b->P, u->b->Q, u->b->interp1d, u->b->grad1d,
-                               u->r->d_offsets, jc, d));
+                               u->r->d_offsets, jc, d, evec));
+  if (evec) CeedChk(rstr_ordered_add(u->r, 1, evec, d));
   return 0;
 }
 int CeedOperatorLinearAssembleDiagonal(CeedOperator op, CeedVector assembled, CeedRequest *request) {
@@ -1361,6 +1453,7 @@ int CeedOperatorDestroy(CeedOperator *op) {
       b200_free(o->qbuf[i]);
     }
     CeedQFunctionDestroy(&o->qf);
+    if (o->xfer_scale) CeedVectorDestroy(&o->xfer_scale);
   }
   Ceed c = o->ceed;
   free(o);

@@ -104,6 +104,7 @@ class GpuLevel:
             elem_nodes = torch.from_numpy(mesh.offsets(1).reshape(-1, 8) // 3).to(self.device)
             vals = torch.zeros(elem_nodes.shape[0] * 576, dtype=torch.float64, device=self.device)
             vec = ceed.Vector(vals.numel())
+            deterministic = ceed.is_deterministic
 
             def values(self):
                 self.vec.set_array(self.vals, level.user.memType)
@@ -155,9 +156,10 @@ class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
     def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg",
-                 assemble="coo", masked=True, overlap=False, halo="nccl"):
+                 assemble="coo", masked=True, overlap=False, halo="nccl", deterministic=False):
         """masked: constrained dofs are masked in L-vector-shaped global vectors (no G2L/L2G copies, see LevelDM);
-        False: compressed PETSc-style global vectors."""
+        False: compressed PETSc-style global vectors.  deterministic: "/gpu/b200:deterministic" -- every transposed
+        restriction sums in the serial /cpu/self order (no FP64 atomics anywhere on the path)."""
         self.app, self.dist = app, dist
         halo_mode = halo
         grid = grid_for(world)
@@ -167,7 +169,7 @@ class Elasticity:
             gmesh = app.mesh
         self.gmesh = gmesh if gmesh is not None else BoxMesh(n=app.n, perturb=app.perturb, seed=0)
         self.mesh = self.gmesh.brick(grid, rank, interface_first=masked and overlap) if world > 1 else self.gmesh
-        self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}")
+        self.ceed = libceed.Ceed(f"/gpu/b200:device_id={device_id}" + (":deterministic" if deterministic else ""))
         self.degrees, self.data, self.phys = setuplibceed.setup_all(self.ceed, self.mesh, app.problem, app.degree, app.nu,
                                                                     app.E, app.qextra, app.multigrid)
         if app.test_mode:

@@ -128,9 +128,10 @@ class LevelDM:
             Xloc.zero_()
             self.global_to_local(X, Xloc)
 
-    def local_to_global(self, Yloc, Y):
-        """VecZeroEntries(Y); DMLocalToGlobal(dm, Yloc, ADD_VALUES, Y): constrained dofs dropped."""
-        if self.halo is not None:
+    def local_to_global(self, Yloc, Y, exchange=True):
+        """VecZeroEntries(Y); DMLocalToGlobal(dm, Yloc, ADD_VALUES, Y): constrained dofs dropped.
+        exchange=False: the interface entries of Yloc are already complete on every rank (injected prolongation)."""
+        if self.halo is not None and (exchange or not self.shared):
             if self.shared:
                 self.halo.sum_and_share(Yloc)
             else:
@@ -201,7 +202,8 @@ def ApplyLocalCeedOp(X, Y, user, zero_xloc=False):
         user.Xceed.set_array(X, user.memType, USE_POINTER)
         user.Yceed.set_array(Y, user.memType, USE_POINTER)
         nif = dm.mesh.n_interface if dm.halo is not None else 0
-        if nif and user.overlap and X.is_cuda and dm.mesh.nelem - nif >= OVERLAP_MIN_INTERIOR:
+        if (nif and user.overlap and X.is_cuda and dm.mesh.nelem - nif >= OVERLAP_MIN_INTERIOR
+                and not user.ceed.is_deterministic):   # the ordered sum runs over the whole restriction
             # partitioned: the elements touching a partition interface come first in the element numbering;
             # once they are done every shared dof holds its complete partial sum, so the halo exchange runs
             # (side stream, NCCL) while the interior elements are processed
@@ -326,9 +328,11 @@ class UserMultProlongRestr:
     opRestrict: object
     ceed: object
     memType: int = MEM_DEVICE
+    fusedScale: object = None   # CeedVector of multVec handed to the fused transfer kernels (None: separate passes)
+    inject: bool = False        # prolongation stores the interpolant (complete on every holder of a node)
 
 
-def setup_prolong_restrict_ctx(dmC, dmF, ceed, dataC, dataF, userC, userF, memType=MEM_DEVICE):
+def setup_prolong_restrict_ctx(dmC, dmF, ceed, dataC, dataF, userC, userF, memType=MEM_DEVICE, fuse_scaling=True):
     """src/misc.c:73-146: shares the level work vectors; multVec = 1 / multiplicity of the fine
     restriction, summed over ranks (L2G then G2L) before the reciprocal (:115-143)."""
     mult_ceed = dataF.Erestrictu.create_vector()
@@ -343,9 +347,20 @@ def setup_prolong_restrict_ctx(dmC, dmF, ceed, dataC, dataF, userC, userF, memTy
             dmF.halo.ghost_to_owner_add(mult)
             dmF.halo.owner_to_ghost(mult)
     multVec = torch.where(mult > 0, 1.0 / mult, mult)
+    fused = None
+    if fuse_scaling and memType == MEM_DEVICE and dataF.opProlong.is_fused and dataF.opRestrict.is_fused:
+        # the fused transfer kernels apply multVec themselves: no VecPointwiseMult passes (matops.c:149,176), and
+        # the prolongation stores the interpolant at every fine node (no atomics, no pre-zeroed output)
+        fused = ceed.Vector(multVec.numel())
+        fused.set_array(multVec, MEM_DEVICE, USE_POINTER)
+        # owner/ghost layouts ADD the ghost copies into the owner afterwards: they need partial sums, not complete values
+        inject = dmF.halo is None or dmF.shared
+        dataF.opProlong.set_transfer_scaling(fused, inject=inject)
+        dataF.opRestrict.set_transfer_scaling(fused)
     return UserMultProlongRestr(dmC=dmC, dmF=dmF, locVecC=userC.Xloc, locVecF=userF.Xloc, multVec=multVec,
                                 ceedVecC=dataC.xceed, ceedVecF=dataF.xceed, opProlong=dataF.opProlong,
-                                opRestrict=dataF.opRestrict, ceed=ceed, memType=memType)
+                                opRestrict=dataF.opRestrict, ceed=ceed, memType=memType, fusedScale=fused,
+                                inject=fused is not None and inject)
 
 
 def _pointwise_mult(w, x, y):
@@ -359,6 +374,19 @@ def Prolong_Ceed(user, X, Y):
     """matops.c:115-157."""
     user.locVecC.zero_()
     user.dmC.global_to_local(X, user.locVecC)
+    if user.fusedScale is not None:
+        # scaling inside the kernel; injected: every fine node is overwritten with the interpolant, complete on every
+        # rank that holds it -> no zeroing, no pointwise product, no halo sum
+        user.ceedVecC.set_array(user.locVecC, user.memType, USE_POINTER)
+        user.ceedVecF.set_array(user.locVecF, user.memType, USE_POINTER)
+        if user.inject:
+            user.opProlong.apply_add(user.ceedVecC, user.ceedVecF)
+        else:
+            user.opProlong.apply(user.ceedVecC, user.ceedVecF)
+        user.ceedVecC.take_array(user.memType)
+        user.ceedVecF.take_array(user.memType)
+        user.dmF.local_to_global(user.locVecF, Y, exchange=not user.inject)
+        return
     user.locVecF.zero_()
     user.ceedVecC.set_array(user.locVecC, user.memType, USE_POINTER)
     user.ceedVecF.set_array(user.locVecF, user.memType, USE_POINTER)
@@ -374,7 +402,8 @@ def Restrict_Ceed(user, X, Y):
     user.locVecF.zero_()
     user.dmF.global_to_local(X, user.locVecF)
     user.locVecC.zero_()
-    _pointwise_mult(user.locVecF, user.locVecF, user.multVec)     # :176
+    if user.fusedScale is None:
+        _pointwise_mult(user.locVecF, user.locVecF, user.multVec)     # :176 (else: inside the fused kernel)
     user.ceedVecF.set_array(user.locVecF, user.memType, USE_POINTER)
     user.ceedVecC.set_array(user.locVecC, user.memType, USE_POINTER)
     user.opRestrict.apply(user.ceedVecF, user.ceedVecC)

@@ -346,6 +346,20 @@ class ChebyshevJacobi:
 # --------------------------------------------------------------------------- coarse level by colouring
 
 
+def _index_add(dst, idx, src, deterministic):
+    """dst[idx[i]] += src[i].  torch's CUDA index_add_ uses FP64 atomics; in deterministic mode the sort-based
+    accumulation of torch is used instead (same order every run)."""
+    if not (deterministic and dst.is_cuda):
+        dst.index_add_(0, idx, src)
+        return
+    prev = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True)
+    try:
+        dst.index_put_((idx.long(),), src, accumulate=True)
+    finally:
+        torch.use_deterministic_algorithms(prev)
+
+
 class ColoredCoarseMatrix:
     """FormJacobian (src/misc.c:151-183): the coarse (p = 1) Jacobian, assembled on the LOCAL vector space of the
     rank and stored as a 27-point block stencil on the node lattice (81 values per row dof); the global action is
@@ -360,6 +374,7 @@ class ColoredCoarseMatrix:
         """coo (optional): object with .elem_nodes (nelem x 8 local node ids, torch, on dm.device) and
         .values() -> nelem*576 element-matrix entries in CeedOperatorLinearAssemble layout."""
         self.dm, self.local_apply, self.coo = dm, local_apply, coo
+        self.deterministic = bool(getattr(coo, "deterministic", False))
         self.coo_dest = None
         self.N = N = dm.mesh.nodes_per_dim(1)
         n, dev = dm.lsize, dm.device
@@ -435,7 +450,7 @@ class ColoredCoarseMatrix:
                 + nodes[:, None, None, :, None] * 3 + cb[None, None, None, None, :]
             self.coo_dest = dest.reshape(-1).to(torch.int32 if 81 * n < 2 ** 31 else torch.int64)
         self.svals.zero_()
-        self.svals.view(-1).index_add_(0, self.coo_dest, self.coo.values())
+        _index_add(self.svals.view(-1), self.coo_dest, self.coo.values(), self.deterministic)
 
     def local_mult(self, xloc, yloc):
         """y_loc = A_loc x_loc (the rank-local, un-assembled matrix)"""
@@ -482,6 +497,7 @@ class SparseCoarseMatrix:
 
     def __init__(self, dm, local_apply, coo=None):
         self.dm, self.local_apply, self.coo = dm, local_apply, coo
+        self.deterministic = bool(getattr(coo, "deterministic", False))
         n, dev = dm.lsize, dm.device
         self.Xloc = torch.zeros(n, dtype=torch.float64, device=dev)
         self.Yloc = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -506,7 +522,7 @@ class SparseCoarseMatrix:
     def assemble(self):
         if self.coo is not None:
             self.vals.zero_()
-            self.vals.index_add_(0, self.dest, self.coo.values())
+            _index_add(self.vals, self.dest, self.coo.values(), getattr(self, "deterministic", False))
             return
         n, dev = self.dm.lsize, self.dm.device
         if n > 20000:

@@ -176,9 +176,22 @@ int b200_diag_accumulate(int nelem, int P, int Q, const double *d_interp1d, cons
  *   gradu            : device, backend strided layout, 9 comps (written; NULL for linElas)
  * Supported: 2 <= P <= Q <= 8 (P, Q as instantiated; see b200_fused_supported). */
 int b200_fused_supported(int P, int Q);
+/* d_evec (all fused kernels): NULL = scatter-add with FP64 atomics straight into the L-vector.  Non-NULL selects
+ * the DETERMINISTIC scatter: the kernel stores its element outputs to d_evec[(e*P^3 + node)*3 + comp] instead
+ * (plain coalesced stores, d_y untouched) and the caller sums them into the L-vector in a fixed order with
+ * b200_transpose_gather_add (layout 1). */
 int b200_apply_residual(int problem, const b200_physics *phys, int nelem, int P, int Q,
                         const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
-                        const double *d_qdata, double *d_gradu, const double *d_x, double *d_y);
+                        const double *d_qdata, double *d_gradu, const double *d_x, double *d_y, double *d_evec);
+
+/* Ordered transpose of an offsets restriction (the serial scatter of /cpu/self, matops.c:46 -> CeedOperatorApply):
+ *   L[o + c*compstride] += sum over the E-vector positions p = e*elemsize + n with offsets[p] == o, ASCENDING p
+ * d_tptr [lsize+1], d_tidx [nelem*elemsize]: CSR of positions by offset value (b200_transpose_map_build).
+ * layout 0: E[(e*ncomp + c)*elemsize + n] (libCEED E-vector);  layout 1: E[(e*elemsize + n)*ncomp + c]. */
+int b200_transpose_gather_add(int lsize, const int *d_tptr, const int *d_tidx, int elemsize, int ncomp, int compstride,
+                              int layout, const double *d_evec, double *d_L);
+/* counting sort of the positions by offset on the HOST (set-up only): tptr [lsize+1], tidx [n] */
+int b200_transpose_map_build(int lsize, size_t n, const int *h_offsets, int *h_tptr, int *h_tidx);
 
 /* Jacobian cache ("jcache"): per quadrature point, everything the Jacobian action needs
  * in its cheapest algebraic form, built from (qdata, gradu) once per linearisation point
@@ -189,12 +202,12 @@ int b200_jcache_build(int problem, int nelem, int Q, const double *d_qdata, cons
                       double *d_jcache);
 int b200_apply_jacobian(int problem, const b200_physics *phys, int nelem, int P, int Q,
                         const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
-                        const double *d_jcache, const double *d_x, double *d_y);
+                        const double *d_jcache, const double *d_x, double *d_y, double *d_evec);
 
 /* CeedOperatorLinearAssembleDiagonal (matops.c:227; App. B.5): diag_L += E^T diag_e */
 int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P, int Q,
                         const double *h_interp1d, const double *h_grad1d, const int *d_offsets,
-                        const double *d_jcache, double *d_diag);
+                        const double *d_jcache, double *d_diag, double *d_evec);
 
 /* ---- halo exchange over NVLink peer memory (one node, one process per GPU; the DMLocalToGlobal(ADD) +
  * DMGlobalToLocal(INSERT) pair of matops.c:33,57 as one symmetric sum-and-share, no communication library on the
@@ -242,10 +255,13 @@ int b200_stencil27_galerkin(int Ncx, int Ncy, int Ncz, const double *d_fine, dou
 /* p-multigrid transfer (matops.c:115-203): out_L += Eo^T I^(T) Ei in_L, identity QFunction,
  * interpolation Pc -> Pf at the fine GLL points; transpose = 1 is the restriction.
  * d_mult (may be NULL): fine-level inverse multiplicity applied to the fine vector
- * (after prolongation / before restriction, matops.c:149,176). */
+ * (after prolongation / before restriction, matops.c:149,176).
+ * inject (prolongation with d_mult only): out_L[fine node] = interpolant, stored instead of summed and scaled --
+ * the elements sharing a fine node all interpolate the same value there (continuous coarse field), so
+ * sum x 1/multiplicity is that value; no atomics, no pre-zeroed output, no read of d_mult. */
 int b200_apply_transfer(int transpose, int nelem, int Pc, int Pf, const double *h_interpCtoF,
-                        const int *d_offc, const int *d_offf, const double *d_mult,
-                        const double *d_in, double *d_out);
+                        const int *d_offc, const int *d_offf, const double *d_mult, int inject,
+                        const double *d_in, double *d_out, double *d_evec);
 
 #ifdef __cplusplus
 }

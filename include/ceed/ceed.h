@@ -182,6 +182,9 @@ CEED_EXTERN int CeedOperatorDestroy(CeedOperator *op);
 /* 1 if the operator's Apply runs as ONE fused kernel (gather..scatter), 0 if generic */
 /* ApplyAdd on the element range [start, stop) of a fused operator (halo-exchange overlap in partitioned runs) */
 CEED_EXTERN int CeedOperatorApplyAddRangeB200(CeedOperator op, CeedVector in, CeedVector out, CeedInt start, CeedInt stop);
+/* fused p-multigrid transfer operators: apply the fine-side inverse-multiplicity scaling of Prolong_Ceed /
+ * Restrict_Ceed (matops.c:149,176) inside the kernel; inject != 0: the prolongation stores the interpolant */
+CEED_EXTERN int CeedOperatorSetTransferScalingB200(CeedOperator op, CeedVector scale, int inject);
 CEED_EXTERN int CeedOperatorIsFusedB200(CeedOperator op, int *isFused);
 /* kernels launched by this library since the last reset (bench.py "gpu_launches") */
 CEED_EXTERN unsigned long long CeedB200LaunchCount(void);

@@ -14,11 +14,11 @@ def dev(a):
 
 class GpuProblem:
     def __init__(self, problem, n, p, perturb=0.08, qextra=0, scale=0.02, multigrid="logarithmic",
-                 node_perm_seed=None, nu=0.3, E=1.0, mesh=None):
+                 node_perm_seed=None, nu=0.3, E=1.0, mesh=None, resource="/gpu/b200"):
         n = (n, n, n) if np.isscalar(n) else n
         self.problem, self.p, self.qextra = problem, p, qextra
         self.mesh = mesh if mesh is not None else BoxMesh(n=n, perturb=perturb, seed=0)
-        self.ceed = libceed.Ceed("/gpu/b200")
+        self.ceed = libceed.Ceed(resource)
         self.perm = None
         if node_perm_seed is not None:
             self.perm = np.random.default_rng(node_perm_seed).permutation(self.mesh.num_nodes(p))

@@ -60,6 +60,25 @@ def test_residual_and_cached_jacobian_match_the_reference_qfunctions(hostlib, ta
     assert _rel(ddv, GOLD[f"{tag}_{name}dF"]) < 5e-13, name
 
 
+@pytest.mark.parametrize("scale", [1e-3, 1e-6, 1e-9])
+@pytest.mark.parametrize("name", ["HyperSS", "HyperFS"])
+def test_residual_keeps_relative_accuracy_at_small_strains(hostlib, name, scale):
+    """The reference avoids cancellation at small strains (log1p series, det C - 1 polynomial: hyperFS.h:45-80); the
+    spatial-form residual of the kernels (tau = mu (b - I) + lambda lnJ I) must do the same: relative error vs the
+    reference QFunction stays at round-off however small the displacement gradient is."""
+    which = oracle.default_which()
+    Q, J, w, ug, _ = make_golden.rnd_inputs(Q=64, seed=5)
+    phys = oracle.Physics(0.3, 1.0)
+    (qd,) = oracle.call_qf("SetupGeo", which, None, Q, [J.reshape(9, Q), w.reshape(1, Q)], [10])
+    du = np.ascontiguousarray(scale * ug.reshape(9, Q))
+    dv_ref, gu_ref = oracle.call_qf(name + "F", which, phys, Q, [du, qd], [9, 9])
+    dv, gradu, ddv = np.zeros((9, Q)), np.zeros((9, Q)), np.zeros((9, Q))
+    assert hostlib.qf_host_resjac(PROBS[name], 0.3, 1.0, Q, _p(du), _p(du), _p(np.ascontiguousarray(qd)), _p(dv), _p(gradu), _p(ddv)) == 0
+    assert np.abs(dv_ref).max() < 10 * scale * np.abs(qd).max() ** 2 * np.abs(ug).max()
+    assert _rel(dv, dv_ref) < 5e-14, (name, scale)
+    assert _rel(gradu, gu_ref) < 5e-14
+
+
 @pytest.mark.parametrize("tag", ["katF", "rnd"])
 @pytest.mark.parametrize("name", list(PROBS))
 def test_closed_form_diagonal_blocks_equal_unit_inputs_through_the_jacobian(hostlib, tag, name):

@@ -146,3 +146,54 @@ def test_errors_are_loud(G):
         op.apply(u, v)
     with pytest.raises(libceed.CeedError):
         c.ElemRestriction(1, 8, 3, 1, 10, np.arange(8) * 3)  # offsets out of range
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_prolong_restrict_with_scaling_inside_the_kernel(G, masked):
+    """Prolong_Ceed / Restrict_Ceed (matops.c:115-203): the fused transfer kernels apply the inverse multiplicity
+    themselves (CeedOperatorSetTransferScalingB200; the prolongation stores the interpolant) -- same result as the
+    reference sequence  operator apply + VecPointwiseMult  and as the oracle."""
+    import torch
+    from ceedpetscsolid_b200 import matops
+    from oracle import oracle
+    g = G.GpuProblem("hyperFS", (3, 4, 2), 4)
+    rng = np.random.default_rng(6)
+    dms = [matops.LevelDM(g.mesh, deg, bc_faces="all", masked=masked) for deg in g.degrees]
+    users = [matops.setup_jacobian_ctx(dms[l], g.ceed, g.data[l], g.phys) for l in range(len(g.degrees))]
+    for level in range(1, len(g.degrees)):
+        pc, pf = g.degrees[level - 1], g.degrees[level]
+        dmC, dmF = dms[level - 1], dms[level]
+        plain = matops.setup_prolong_restrict_ctx(dmC, dmF, g.ceed, g.data[level - 1], g.data[level], users[level - 1],
+                                                  users[level], fuse_scaling=False)
+        Xc, Xf = dmC.create_global_vector(), dmF.create_global_vector()
+        Xc.copy_(torch.from_numpy(rng.standard_normal(dmC.nglobal))); dmC.zero_constrained(Xc)
+        Xf.copy_(torch.from_numpy(rng.standard_normal(dmF.nglobal))); dmF.zero_constrained(Xf)
+        Yf0, Yc0 = dmF.create_global_vector(), dmC.create_global_vector()
+        assert plain.fusedScale is None
+        matops.Prolong_Ceed(plain, Xc, Yf0)
+        matops.Restrict_Ceed(plain, Xf, Yc0)
+        fused = matops.setup_prolong_restrict_ctx(dmC, dmF, g.ceed, g.data[level - 1], g.data[level], users[level - 1],
+                                                  users[level])
+        assert fused.fusedScale is not None and fused.inject
+        Yf1, Yc1 = dmF.create_global_vector(), dmC.create_global_vector()
+        fused.locVecF.fill_(123.0)   # injected prolongation needs no zeroed work vector
+        matops.Prolong_Ceed(fused, Xc, Yf1)
+        matops.Restrict_Ceed(fused, Xf, Yc1)
+        torch.cuda.synchronize()
+        assert rel_err(Yf1.cpu().numpy(), Yf0.cpu().numpy()) < TOL
+        assert rel_err(Yc1.cpu().numpy(), Yc0.cpu().numpy()) < TOL
+        # oracle: interpolate the coarse L-vector, scale by the inverse multiplicity
+        offc, offf = g.mesh.offsets(pc), g.mesh.offsets(pf)
+        lc, lf = g.mesh.lsize(pc), g.mesh.lsize(pf)
+        xc_l = np.zeros(lc)
+        freeC, freeF = ~np.repeat(dmC.bc_nodes, 3), ~np.repeat(dmF.bc_nodes, 3)
+        xc_l[freeC] = Xc.cpu().numpy()[freeC] if masked else Xc.cpu().numpy()
+        mult = oracle.multiplicity(g.mesh.nelem, (pf + 1) ** 3, 3, lf, offf)
+        yo = oracle.transfer(False, g.mesh.nelem, pc + 1, pf + 1, offc, offf, xc_l, lf) / mult
+        got = Yf1.cpu().numpy()
+        assert rel_err(got[freeF] if masked else got, yo[freeF]) < TOL
+        # plain operator semantics are restored when the scaling is removed
+        g.data[level].opProlong.set_transfer_scaling(None)
+        g.data[level].opRestrict.set_transfer_scaling(None)
+        c = rng.standard_normal(lc)
+        assert rel_err(g.apply(g.data[level].opProlong, c, lf), oracle.transfer(False, g.mesh.nelem, pc + 1, pf + 1, offc, offf, c, lf)) < TOL

@@ -62,15 +62,19 @@ def test_newton_krylov_pmg_converges_on_the_oracle(problem, degree, steps, maske
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("deterministic", [False, True], ids=["atomics", "deterministic"])
 @pytest.mark.parametrize("problem,degree,n,steps,masked", [("hyperFS", 2, (4, 4, 4), 2, True), ("hyperSS", 3, (3, 3, 3), 1, True),
                                                            ("hyperFS", 4, (2, 2, 3), 2, True), ("hyperFS", 2, (4, 4, 4), 2, False)])
-def test_gpu_and_oracle_agree_on_iteration_counts_and_solution(problem, degree, n, steps, masked):
+def test_gpu_and_oracle_agree_on_iteration_counts_and_solution(problem, degree, n, steps, masked, deterministic):
+    """deterministic: "/gpu/b200:deterministic" -- every transposed restriction sums in the serial /cpu/self order
+    (matops.c:46 behind CeedOperatorApply), so the iteration counts do not rest on FP64 atomics being benign."""
     from ceedpetscsolid_b200.elasticity import Elasticity
     from oracle_levels import oracle_solve
     app = AppCtx(problem=problem, degree=degree, n=n, num_steps=steps, perturb=0.05,
                  clamp={(2, 0): [0, 0, 0, 0, 0, 1, 0], (2, 1): [0.01, 0, -0.04, 0, 0, 1, 0.02]})
     ref, Uref = oracle_solve(app, masked=masked)
-    el = Elasticity(app, masked=masked)
+    el = Elasticity(app, masked=masked, deterministic=deterministic)
+    assert el.ceed.is_deterministic == deterministic
     out = el.solve()
     assert out["converged"] and ref["converged"]
     assert out["snes_its"] == ref["snes_its"], (out, ref)
