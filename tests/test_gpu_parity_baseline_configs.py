@@ -27,12 +27,32 @@ def test_full_size_residual_jacobian_diagonal_match_the_oracle(problem, n, p):
     g = G.GpuProblem(problem, n, p)
     o = OracleProblem(problem, n, p)
     assert o.nelem == n ** 3 and g.fine.opApply.is_fused
-    # residual on the fine level + the stored displacement gradient
-    yo = o.residual_fine(o.u_fine)
-    assert rel_err(g.residual(), yo) < TOL
+    # residual on the fine level + the stored displacement gradient.
+    # (i) State with nodal noise on top of the smooth field: the assembled residual is as large as the element
+    #     contributions it is summed from -> plain relative error.
+    rng = np.random.default_rng(2)
+    u_rough = o.u_fine + 2e-5 * rng.standard_normal(o.u_fine.size)
+    yo = o.residual_fine(u_rough)
+    e_rough = rel_err(g.residual(u_rough), yo)
+    # (ii) The smooth state of SURVEY 8(d).  On a mesh this fine the residual map is ill-conditioned in its input:
+    #     the displacement gradient comes from differences of neighbouring nodal values (|u| ~ 0.03, differences ~ h |grad u|),
+    #     so perturbing every nodal value by ONE ulp already moves the oracle's own residual by 2.5e-13 (32^3) to
+    #     ~7e-13 (64^3) relative.  Two backward-stable evaluations can therefore differ by a few times that; the
+    #     sensitivity is measured here with the oracle and bounds the comparison (the Jacobian has no such
+    #     amplification: 2e-16 for the same perturbation).
+    yo = o.residual_fine(o.u_fine).copy()
+    yg = g.residual()
+    sgn = rng.choice([-1.0, 1.0], o.u_fine.size)
+    s1 = rel_err(o.residual_fine(o.u_fine * (1.0 + 1.1e-16 * sgn)), yo)
+    o.residual_fine(o.u_fine)      # restores gradu at the unperturbed state
+    e_smooth = rel_err(yg, yo)
+    print(f"{problem} {n}^3 residual: rough state {e_rough:.2e}; smooth state {e_smooth:.2e} "
+          f"(oracle moves by {s1:.2e} under 1-ulp input noise)")
+    assert e_rough < TOL
+    assert e_smooth < max(TOL, 8 * s1)
     gu = g.strided_to_plain(g.fine.ErestrictGradui, g.fine.gradu)
     assert rel_err(gu, o.gradu) < TOL
-    del gu, yo
+    del gu, yo, yg
     # Jacobian + diagonal on every level (all levels integrate on the fine quadrature data)
     rng = np.random.default_rng(1)
     for level, deg in enumerate(g.degrees):
