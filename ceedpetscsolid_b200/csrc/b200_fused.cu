@@ -857,6 +857,19 @@ extern "C" int b200_fused_supported(int P, int Q) {
   return 0;
 }
 
+// shared-memory lattice strides of the fused apply kernel for (P, Q): out = {SY, SZ, SC, SE, EB, NT}
+extern "C" int b200_apply_smem_layout(int P, int Q, int *out) {
+#define X(p, q)                                                                                   \
+  if (P == p && Q == q) {                                                                         \
+    out[0] = Cfg<q>::SY; out[1] = Cfg<q>::SZ; out[2] = apply_sc(p, q); out[3] = apply_se(q, apply_sc(p, q)); \
+    out[4] = Cfg<q>::EB; out[5] = Cfg<q>::NT;                                                     \
+    return 0;                                                                                     \
+  }
+  B200_FOR_PQ(X)
+#undef X
+  return set_error_msg("b200_apply_smem_layout: (P,Q) not instantiated");
+}
+
 extern "C" int b200_jcache_ncomp(int problem) {
   return problem == B200_PROB_LINELAS ? 9 : problem == B200_PROB_HYPERSS ? 10 : problem == B200_PROB_HYPERFS ? 16 : -1;
 }

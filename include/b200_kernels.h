@@ -176,6 +176,9 @@ int b200_diag_accumulate(int nelem, int P, int Q, const double *d_interp1d, cons
  *   gradu            : device, backend strided layout, 9 comps (written; NULL for linElas)
  * Supported: 2 <= P <= Q <= 8 (P, Q as instantiated; see b200_fused_supported). */
 int b200_fused_supported(int P, int Q);
+/* shared-memory lattice of the fused apply kernel (tests: bank-conflict freedom): out[6] = {stride y, stride z,
+ * component stride, element stride (all in doubles), elements per CTA, threads per CTA} */
+int b200_apply_smem_layout(int P, int Q, int *out);
 /* d_evec (all fused kernels): NULL = scatter-add with FP64 atomics straight into the L-vector.  Non-NULL selects
  * the DETERMINISTIC scatter: the kernel stores its element outputs to d_evec[(e*P^3 + node)*3 + comp] instead
  * (plain coalesced stores, d_y untouched) and the caller sums them into the L-vector in a fixed order with
