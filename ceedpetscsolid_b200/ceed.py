@@ -107,6 +107,7 @@ _proto("CeedOperatorDestroy", _pvp)
 _proto("CeedOperatorIsFusedB200", _vp, C.POINTER(_i))
 _proto("CeedOperatorApplyAddRangeB200", _vp, _vp, _vp, _i, _i)
 _proto("CeedOperatorSetTransferScalingB200", _vp, _vp, _i)
+_proto("CeedOperatorApplyPartitionedB200", _vp, _vp, _vp, _i, _vp, _vp, _i)
 _proto("CeedIsDeterministic", _vp, _vp)
 _proto("CeedB200LaunchCount", restype=C.c_ulonglong)
 _proto("CeedB200LaunchCountReset", restype=None)
@@ -146,8 +147,13 @@ _proto("b200_fp64_probe", C.POINTER(_d))
 _proto("b200_ipc_get_handle", _vp, _vp)
 _proto("b200_ipc_open", _vp, _pvp)
 _proto("b200_ipc_close", _vp)
-_proto("b200_halo_push_signal", _i, _vp, _vp, _vp, _vp, _vp, C.c_longlong)
-_proto("b200_halo_wait_unpack", _i, _vp, C.c_longlong, _vp, _vp, _vp, _sz, _vp, _d)
+_proto("b200_halo_window_bytes", _sz, restype=_sz)
+_proto("b200_halo_create", _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _d, _pvp)
+_proto("b200_halo_destroy", _vp)
+_proto("b200_halo_begin", _vp, _vp)
+_proto("b200_halo_end", _vp, _vp)
+_proto("b200_halo_error", _vp, _vp)
+_proto("b200_halo_unpack_ordered", _i, _vp, _vp, _vp, _vp, _vp)
 _proto("b200_lattice_prolong", _i, _i, _i, _vp, _vp)
 _proto("b200_lattice_restrict", _i, _i, _i, _vp, _vp)
 _proto("b200_cheb_init", _vp, _vp, _vp, _vp, _d, _i, _sz)
@@ -448,6 +454,14 @@ class Operator(_Obj):
 
     def apply_add_range(self, u, v, start, stop):
         self._chk(lib.CeedOperatorApplyAddRangeB200(self.h, u.h, v.h, int(start), int(stop)))
+
+    def apply_partitioned(self, u, v, n_interface, halo_handle, mask_idx):
+        """CeedOperatorApplyPartitionedB200: v = 0; interface elements; halo exchange overlapped with the interior
+        elements; ordered sum; zero the entries mask_idx (int32 device tensor or None)."""
+        self._chk(lib.CeedOperatorApplyPartitionedB200(
+            self.h, u.h, v.h, int(n_interface), halo_handle,
+            mask_idx.data_ptr() if mask_idx is not None and mask_idx.numel() else None,
+            int(mask_idx.numel()) if mask_idx is not None else 0))
 
     def set_transfer_scaling(self, scale, inject=False):
         """CeedOperatorSetTransferScalingB200: fused transfer operators apply the fine-side inverse multiplicity

@@ -24,6 +24,7 @@
 // around the unmodified QFunction.  See DESIGN.md for the roofline arithmetic.
 #include "b200_qf.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace b200 {
@@ -59,7 +60,11 @@ template <int Q> struct Cfg {
 // ideal, 188 unpadded; tools/smem_pad.py, checked in tests/test_abi_and_layout.py).  No pad helps the other pairs.
 __host__ __device__ constexpr int odd_extent(int Q) { return (Q % 2) ? Q : Q + 1; }
 __host__ __device__ constexpr int apply_sc(int P, int Q) {
+#ifdef B200_NO_SCPAD
+  return odd_extent(Q) * odd_extent(Q) * odd_extent(Q);
+#else
   return odd_extent(Q) * odd_extent(Q) * odd_extent(Q) + ((P == 5 && Q == 5) ? 14 : 0);
+#endif
 }
 __host__ __device__ constexpr int apply_se(int Q, int SC) {
   return elems_per_block(Q) == 16 ? ((9 * SC) | 1) : 9 * SC + ((16 / elems_per_block(Q) - (9 * SC) % 16) + 16) % 16;
@@ -356,6 +361,15 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
     unsigned u[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; it++) u[it] = (FULL && (it + 1) * NT <= EB * 3 * P3) || (tid + it * NT < total) ? __ldg(scat_tab + tid + it * NT) : 0u;
+#ifdef B200_NO_BATCH_SCATTER
+    if (!evec) {
+#pragma unroll
+      for (int it = 0; it < NIT; it++)
+        if (tid + it * NT < total)
+          atomicAdd(y + soff[(u[it] >> 16) & 0xFFFu] + (u[it] >> 28), smem[u[it] & 0xFFFFu]);
+      return;
+    }
+#endif
     double val[NIT];
     int dst[NIT];
 #pragma unroll
@@ -761,9 +775,17 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
     pd.configured[dev] = true;
   }
   const unsigned *d_tab = static_cast<const unsigned *>(pd.table[dev]);
+#ifdef B200_NO_FULL
+  if (nelem) {
+    kern_tail<<<(nelem + EB - 1) / EB, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y, d_tab, 0, evec);
+    B200_LAUNCH_CHECK("k_fused_apply");
+    return 0;
+  }
+#endif
+  static const int ahead = getenv("B200_OFFSETS_AHEAD") ? atoi(getenv("B200_OFFSETS_AHEAD")) : OFFSETS_AHEAD;
   const int nfull = nelem / EB, ntail = nelem - nfull * EB;
   if (nfull) {
-    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, OFFSETS_AHEAD, evec);
+    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, ahead, evec);
     B200_LAUNCH_CHECK("k_fused_apply");
   }
   if (ntail) {  // the partial group at the end of the element range: same kernel with run-time group extent

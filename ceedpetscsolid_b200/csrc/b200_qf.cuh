@@ -374,6 +374,21 @@ B200_DI void jacobian_point(const Material &mt, const double *jc, const double (
     hyperss_df_point(mt, 1., A, jc[9], H, W);
   } else {
     // A holds K' here
+#ifdef B200_OLD_JPOINT
+    double gt[3][3], Z[3][3], bm[3][3];
+    const double bv[6] = {jc[9], jc[10], jc[11], jc[12], jc[13], jc[14]};
+    voigt_sym(bv, bm);
+    phys_grad(A, H, gt);
+    const double cw = mt.mu, bw = mt.mu - mt.lambda * jc[15];
+    const double aw = mt.lambda * (gt[0][0] + gt[1][1] + gt[2][2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        Z[c][j] = cw * (gt[c][0] * bm[0][j] + gt[c][1] * bm[1][j] + gt[c][2] * bm[2][j]) + bw * gt[j][c] +
+                  (c == j ? aw : 0.);
+    pull_back(A, Z, W);
+#else
     double gt[3][3], Z[3][3], bm[3][3];
     // mu folded into b once (6 multiplies) so that every entry of Z is one multiply-or-fma start + 3 fma
     const double bv[6] = {mt.mu * jc[9], mt.mu * jc[10], mt.mu * jc[11], mt.mu * jc[12], mt.mu * jc[13], mt.mu * jc[14]};
@@ -391,6 +406,7 @@ B200_DI void jacobian_point(const Material &mt, const double *jc, const double (
         Z[c][j] = fma(gt[c][2], bm[2][j], z);
       }
     pull_back(A, Z, W);  // W[c][k] = sum_m K'[k][m] Z[c][m]
+#endif
   }
 }
 

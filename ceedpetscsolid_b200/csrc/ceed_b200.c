@@ -1329,6 +1329,41 @@ int CeedOperatorSetTransferScalingB200(CeedOperator op, CeedVector scale, int in
   return 0;
 }
 
+/* /gpu/b200 extension: the whole partitioned MatShell MatMult of ApplyLocalCeedOp (matops.c:26-60) in the masked
+ * layout, issued from C in one call:
+ *     out = 0;  out += A_loc in on the elements [0, n_interface) that touch a partition interface;
+ *     halo exchange starts on its side stream (b200_halo_begin: interface partial sums are complete);
+ *     out += A_loc in on the interior elements [n_interface, nelem)   -- overlaps the exchange;
+ *     b200_halo_end: ordered sum of the holders' partial sums;  zero the Dirichlet rows d_mask[0..nmask).
+ * halo may be NULL (single rank).  In deterministic mode (no element-range applies) the operator runs as a whole
+ * and the exchange follows it. */
+int CeedOperatorApplyPartitionedB200(CeedOperator op, CeedVector in, CeedVector out, CeedInt n_interface, void *halo,
+                                     const CeedInt *d_mask, CeedInt nmask) {
+  Ceed ceed = op->ceed;
+  if (op->composite) return CeedError(ceed, 1, "CeedOperatorApplyPartitionedB200: composite operators are not supported");
+  if (op->kind == OP_UNSET) CeedChk(op_setup(op));
+  if (op->kind != OP_FUSED_JACOBIAN && op->kind != OP_FUSED_RESIDUAL)
+    return CeedError(ceed, 1, "CeedOperatorApplyPartitionedB200: operator %s does not run on the fused kernels", op->qf->name);
+  const int nelem = op->in[0].r->nelem, EB = b200_elems_per_block(op->in[0].b->Q);
+  if (n_interface < 0 || n_interface > nelem || (n_interface % EB && n_interface != nelem))
+    return CeedError(ceed, 1, "CeedOperatorApplyPartitionedB200: n_interface %d must be a multiple of %d within [0, %d]", n_interface, EB, nelem);
+  double *y;
+  CeedChk(CeedVectorSetValue(out, 0.0));
+  if (!halo || ceed->deterministic || n_interface == 0 || n_interface == nelem) {
+    CeedChk(op_apply_fused_range(op, in, out, 0, nelem));
+    CeedChk(vec_dev_rw(out, &y));
+    if (halo) { B2(ceed, b200_halo_begin((b200_halo *)halo, y)); B2(ceed, b200_halo_end((b200_halo *)halo, y)); }
+  } else {
+    CeedChk(op_apply_fused_range(op, in, out, 0, n_interface));
+    CeedChk(vec_dev_rw(out, &y));
+    B2(ceed, b200_halo_begin((b200_halo *)halo, y));
+    CeedChk(op_apply_fused_range(op, in, out, n_interface, nelem));
+    B2(ceed, b200_halo_end((b200_halo *)halo, y));
+  }
+  if (nmask > 0) B2(ceed, b200_mask_zero(y, d_mask, (size_t)nmask));
+  return 0;
+}
+
 /* libCEED interface semantics: zero every output (active and passive), then ApplyAdd */
 int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
   if (op->composite) {

@@ -156,7 +156,7 @@ class Elasticity:
     """Builds the whole solver stack for one rank (one GPU)."""
 
     def __init__(self, app, dist=None, rank=0, world=1, device_id=0, gmesh=None, coarse_rtol=1e-2, coarse="hmg",
-                 assemble="coo", masked=True, overlap=False, halo="nccl", deterministic=False):
+                 assemble="coo", masked=True, overlap=True, halo="p2p", deterministic=False):
         """masked: constrained dofs are masked in L-vector-shaped global vectors (no G2L/L2G copies, see LevelDM);
         False: compressed PETSc-style global vectors.  deterministic: "/gpu/b200:deterministic" -- every transposed
         restriction sums in the serial /cpu/self order (no FP64 atomics anywhere on the path)."""
@@ -226,6 +226,7 @@ class Elasticity:
                 self.V.weights[dm.nglobal] = dm.dot_weight
             if dm.dot_weight is not None or dm.masked:
                 self.V.consistent[dm.nglobal] = dm.make_consistent
+        self.all_dms = self.dms + list(h_dms or [])
         self.pc = solver.PMultigrid(self.V, self.levels, self.transfers, coarse_rtol=coarse_rtol, h_dms=h_dms)
         self.U = self.dms[fine].create_global_vector()
 
@@ -257,11 +258,25 @@ class Elasticity:
     def solve(self, log=None, **kw):
         self.U.zero_()
         fine = self.levels[-1]
-        out = solver.newton_solve(self.V, fine, self.pc, self.U, num_increments=self.app.num_steps, log=log, **kw)
+        out = solver.newton_solve(self.V, fine, self.pc, self.U, num_increments=self.app.num_steps, log=log,
+                                  check=self.check_halos, **kw)
+        self.check_halos()
         out["dofs_global_unconstrained"] = self._global_unconstrained()
         # "DoFs/Sec in SNES" = global dofs x total KSP iterations / solve time (elasticity.c:762-764), in MDoF/s
         out["mdofs_per_sec_in_snes"] = 1e-6 * out["dofs_global_unconstrained"] * out["ksp_its"] / max(out["time_s"], 1e-12)
         return out
+
+    def check_halos(self):
+        """Raises if a peer-memory halo exchange of any level timed out (Halo.check_p2p; synchronises)."""
+        for dm in self.all_dms:
+            if dm.halo is not None:
+                dm.halo.check_p2p()
+
+    def close(self):
+        """Collective: release the peer-memory windows of every level."""
+        for dm in self.all_dms:
+            if dm.halo is not None:
+                dm.halo.close()
 
     def strain_energy(self):
         """elasticity.c:820-830: strain energy of the current state at full load (ComputeStrainEnergy)."""

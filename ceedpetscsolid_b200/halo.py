@@ -102,6 +102,25 @@ class Halo:
         # "sum-and-share": every dof shared with r, both directions at once (same order on both sides)
         self.shared_all = {r: torch.from_numpy(dofs(shared[r])).to(self.device) for r in self.neighbours}
         self.share_cat, self.share_views = layout(self.shared_all)
+        # canonical summation order of the sum-and-share: for every unique shared dof, the holders' partial sums in
+        # ASCENDING RANK order, this rank's own (entry -1) included; the other entries are positions of the receive
+        # buffer / window (laid out like share_cat).  Every holder then computes the bit-identical total.
+        cat = self.share_cat.cpu().numpy().astype(np.int64)
+        src_rank = np.concatenate([np.full(self.shared_all[r].numel(), r, dtype=np.int64) for r in self.neighbours]) \
+            if self.neighbours else np.zeros(0, dtype=np.int64)
+        udof = np.unique(cat)
+        dof_all = np.concatenate([cat, udof])
+        rank_all = np.concatenate([src_rank, np.full(udof.size, rank, dtype=np.int64)])
+        ent_all = np.concatenate([np.arange(cat.size, dtype=np.int64), np.full(udof.size, -1, dtype=np.int64)])
+        order = np.lexsort((rank_all, dof_all))
+        counts = np.bincount(np.searchsorted(udof, dof_all), minlength=udof.size)
+        uptr = np.zeros(udof.size + 1, dtype=np.int64)
+        np.cumsum(counts, out=uptr[1:])
+        self._udof_h, self._uptr_h, self._uent_h = udof, uptr, ent_all[order]
+        self.udof = torch.from_numpy(udof.astype(np.int32)).to(self.device)
+        self.uptr = torch.from_numpy(uptr.astype(np.int32)).to(self.device)
+        self.uent = torch.from_numpy(self._uent_h.astype(np.int32)).to(self.device)
+        self._ordered_cpu = None
         # number of ranks holding each local node (1 in the interior)
         cnt = np.ones(self.nnodes)
         for r in self.neighbours:
@@ -154,22 +173,51 @@ class Halo:
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+        if add is None:
+            return rbuf
         self._scatter(vec, recv_cat, rbuf, add)
 
+    def _unpack_ordered(self, Yloc, rbuf):
+        """Yloc[shared dof] = sum of the holders' partial sums in ascending rank order (own partial sum = current value)."""
+        if self.udof.numel() == 0:
+            return
+        if Yloc.is_cuda:
+            from .ceed import b2, lib
+            b2(lib.b200_halo_unpack_ordered(self.udof.numel(), self.udof.data_ptr(), self.uptr.data_ptr(),
+                                            self.uent.data_ptr(), rbuf.data_ptr(), Yloc.data_ptr()))
+            return
+        if self._ordered_cpu is None:
+            cnt = np.diff(self._uptr_h)
+            pad = np.full((self._udof_h.size, int(cnt.max())), -2, dtype=np.int64)
+            col = np.arange(self._uent_h.size) - np.repeat(self._uptr_h[:-1], cnt)
+            pad[np.repeat(np.arange(self._udof_h.size), cnt), col] = self._uent_h
+            self._ordered_cpu = (torch.from_numpy(self._udof_h), torch.from_numpy(pad))
+        udof, pad = self._ordered_cpu
+        own = Yloc[udof]
+        s = torch.zeros_like(own)
+        for k in range(pad.shape[1]):
+            e = pad[:, k]
+            s = s + torch.where(e == -1, own, torch.where(e >= 0, rbuf[e.clamp(min=0)], torch.zeros_like(own)))
+        Yloc[udof] = s
+
     # ---- sum-and-share over NVLink peer memory (one node): no communication library on the data path
-    def enable_p2p(self, timeout_s=5.0):
+    def enable_p2p(self, timeout_s=None):
         """Collective over all ranks: allocate this rank's receive window, exchange CUDA IPC handles and segment
-        layouts through torch.distributed (set-up only), map the neighbours' windows.  Afterwards sum_and_share
-        is three kernels of libceed_b200.so (csrc/b200_halo.cu): store the packed partial sums into the
-        neighbours' windows, flag them, wait for the neighbours' flags and add the own window."""
+        layouts through torch.distributed (set-up only), map the neighbours' windows and create the C-side exchange
+        object (csrc/b200_halo.cu).  Afterwards sum_and_share is push + signal on a high-priority side stream and
+        wait + ordered unpack on the compute stream; `handle` can be given to CeedOperatorApplyPartitionedB200,
+        which overlaps the exchange with the interior elements.  timeout_s (default $B200_HALO_TIMEOUT_S or 20):
+        how long a rank waits for a neighbour before it flags the exchange as failed (check_p2p raises)."""
         import ctypes as C
+        import os
         from .ceed import b2, lib
         dist = self.dist
         assert self.device.type == "cuda", "peer-memory halo needs CUDA tensors"
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("B200_HALO_TIMEOUT_S", "20"))
         total = int(self.share_cat.numel())
-        nflags = 64
+        nbytes = int(lib.b200_halo_window_bytes(total))
         buf = C.c_void_p()
-        nbytes = 2 * total * 8 + nflags * 8 + 8
         b2(lib.b200_malloc(C.byref(buf), nbytes))
         b2(lib.b200_memset(buf, 0, nbytes))
         b2(lib.b200_sync())
@@ -196,10 +244,18 @@ class Halo:
             for par in (0, 1):
                 remote[par][s] = base.value + (par * info["total"] + ra) * 8
             rflag[s] = base.value + 2 * info["total"] * 8 + info["neighbours"].index(self.rank) * 8
-        self._p2p = dict(buf=buf, total=total, nn=nn, seg_start=seg_start, remote=remote, rflag=rflag, gen=0,
-                         flags=buf.value + 2 * total * 8, err=buf.value + 2 * total * 8 + nflags * 8,
-                         timeout=float(timeout_s))
+        h = C.c_void_p()
+        b2(lib.b200_halo_create(nn, seg_start, remote[0], remote[1], rflag, self.share_cat.data_ptr(), total, buf,
+                                self.udof.numel(), self.udof.data_ptr(), self.uptr.data_ptr(), self.uent.data_ptr(),
+                                float(timeout_s), C.byref(h)))
+        self._p2p = dict(buf=buf, handle=h)
         dist.barrier()   # every window is mapped before anyone pushes
+
+    @property
+    def handle(self):
+        """b200_halo* of the peer-memory exchange (None unless enable_p2p was called)."""
+        p = getattr(self, "_p2p", None)
+        return p["handle"] if p is not None else None
 
     def check_p2p(self):
         """Raises if a peer-memory exchange ever timed out (synchronises the device)."""
@@ -208,29 +264,40 @@ class Halo:
         import ctypes as C
         from .ceed import b2, lib
         e = C.c_int(0)
-        b2(lib.b200_memcpy_d2h(C.byref(e), C.c_void_p(self._p2p["err"]), 4))
+        b2(lib.b200_halo_error(self._p2p["handle"], C.byref(e)))
         if e.value:
-            raise RuntimeError("peer-memory halo exchange timed out waiting for a neighbour")
+            raise RuntimeError("peer-memory halo exchange timed out waiting for a neighbour: the vectors it produced "
+                               "are incomplete")
+
+    def close(self):
+        """Collective: unmap the neighbours' windows and free this rank's (after every rank is done with them)."""
+        p = getattr(self, "_p2p", None)
+        if p is None:
+            return
+        from .ceed import b2, lib
+        b2(lib.b200_sync())
+        self.dist.barrier()
+        b2(lib.b200_halo_destroy(p["handle"]))
+        for base in self._p2p_open:
+            b2(lib.b200_ipc_close(base))
+        self.dist.barrier()
+        b2(lib.b200_free(p["buf"]))
+        self._p2p, self._p2p_open = None, []
 
     def _sum_and_share_p2p(self, Yloc):
         from .ceed import b2, lib
-        p = self._p2p
-        p["gen"] += 1
-        g = p["gen"]
-        par = g & 1
-        b2(lib.b200_halo_push_signal(p["nn"], p["seg_start"], p["remote"][par], p["rflag"], self.share_cat.data_ptr(),
-                                     Yloc.data_ptr(), g))
-        b2(lib.b200_halo_wait_unpack(p["nn"], p["flags"], g, self.share_cat.data_ptr(),
-                                     p["buf"].value + par * p["total"] * 8, Yloc.data_ptr(), p["total"], p["err"],
-                                     p["timeout"]))
+        b2(lib.b200_halo_begin(self._p2p["handle"], Yloc.data_ptr()))
+        b2(lib.b200_halo_end(self._p2p["handle"], Yloc.data_ptr()))
 
     def sum_and_share(self, Yloc):
         """One symmetric exchange replacing ghost->owner ADD followed by owner->ghost INSERT: every rank
-        sends its partial sums on ALL shared dofs to every sharer and adds what it receives, so all copies
-        end up with the assembled value (allowed harness optimisation)."""
+        sends its partial sums on ALL shared dofs to every sharer and sums what it holds and receives in ascending
+        rank order, so all copies end up with the same assembled value, bit for bit (allowed
+        harness optimisation)."""
         if getattr(self, "_p2p", None) is not None and Yloc.is_cuda:
             return self._sum_and_share_p2p(Yloc)
-        self._exchange(Yloc, self.share_cat, self.share_views, self.share_cat, self.share_views, add=True, tag="sas")
+        rbuf = self._exchange(Yloc, self.share_cat, self.share_views, self.share_cat, self.share_views, add=None, tag="sas")
+        self._unpack_ordered(Yloc, rbuf)
 
     # ---- split form of sum_and_share: the exchange runs on a side stream while the caller keeps computing on
     # entries that are NOT shared (the interior elements of an operator application)
@@ -274,7 +341,7 @@ class Halo:
         else:
             for w in pend[2]:
                 w.wait()
-        self._scatter(Yloc, self.share_cat, pend[1], True)
+        self._unpack_ordered(Yloc, pend[1])
 
     def owner_to_ghost(self, Xloc):
         """DMGlobalToLocal part 2: ghosts receive the owner's value."""

@@ -183,6 +183,7 @@ class UserMult:
     loadIncrement: float = 1.0
     bc_values: object = None  # callable(loadIncrement) -> tensor over dm.bc_idx, or None
     overlap: bool = True      # partitioned + masked layout: overlap the halo exchange with the interior elements
+    fused: object = None      # cached CeedOperatorIsFusedB200(op)
 
 
 def setup_jacobian_ctx(dm, ceed, data, phys, physSmoother=None, memType=MEM_DEVICE):
@@ -201,6 +202,17 @@ def ApplyLocalCeedOp(X, Y, user, zero_xloc=False):
         # into -- no DMGlobalToLocal / DMLocalToGlobal data movement at all
         user.Xceed.set_array(X, user.memType, USE_POINTER)
         user.Yceed.set_array(Y, user.memType, USE_POINTER)
+        if user.fused is None:
+            user.fused = bool(user.op.is_fused)
+        if X.is_cuda and user.fused and (dm.halo is None or dm.halo.handle is not None):
+            # the whole MatMult in one C call: zero Y, interface elements, peer-memory halo exchange overlapped with
+            # the interior elements, ordered sum of the holders' partial sums, zero the Dirichlet rows
+            nif = dm.mesh.n_interface if (dm.halo is not None and user.overlap) else 0
+            user.op.apply_partitioned(user.Xceed, user.Yceed, nif, dm.halo.handle if dm.halo is not None else None,
+                                      dm.bc_idx)
+            user.Xceed.take_array(user.memType)
+            user.Yceed.take_array(user.memType)
+            return
         nif = dm.mesh.n_interface if dm.halo is not None else 0
         if (nif and user.overlap and X.is_cuda and dm.mesh.nelem - nif >= OVERLAP_MIN_INTERIOR
                 and not user.ceed.is_deterministic):   # the ordered sum runs over the whole restriction

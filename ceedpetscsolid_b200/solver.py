@@ -786,8 +786,9 @@ class PMultigrid:
 
 
 def newton_solve(V, fine, pc, U, num_increments=10, snes_rtol=1e-8, snes_atol=1e-50, snes_maxit=50, ksp_rtol=1e-10,
-                 ksp_maxit=200, log=None):
-    """Load-increment loop + Newton (elasticity.c:637-673).  fine.residual(U, F, load) evaluates
+                 ksp_maxit=200, log=None, check=None):
+    """Load-increment loop + Newton (elasticity.c:637-673).  check (optional): called after every linear solve, at a
+    point where the host has just synchronised -- the harness uses it to fail loudly on a timed-out halo exchange.  fine.residual(U, F, load) evaluates
     FormResidual_Ceed at load fraction `load` (and refreshes gradu); the Jacobian operators then
     linearise about that state.  Returns a summary dict (iteration counts as in elasticity.c:684-749)."""
     n, dev = fine.n, fine.device
@@ -809,6 +810,8 @@ def newton_solve(V, fine, pc, U, num_increments=10, snes_rtol=1e-8, snes_atol=1e
         fnorm0 = math.sqrt(V.dot(F, F))  # scale of the increment: reference for the relative tolerance
         dU.zero_()
         k, reason, _ = pcg(V, fine.jacobian, F, dU, M=pc.apply, rtol=ksp_rtol, maxit=ksp_maxit, work=work)
+        if check:
+            check()
         V.axpy(U, -1.0, dU)
         total_ksp += k
         fine.residual(U, F, load)
@@ -820,6 +823,8 @@ def newton_solve(V, fine, pc, U, num_increments=10, snes_rtol=1e-8, snes_atol=1e
             pc.setup()
             dU.zero_()
             k, reason, _ = pcg(V, fine.jacobian, F, dU, M=pc.apply, rtol=ksp_rtol, maxit=ksp_maxit, work=work)
+            if check:
+                check()
             # backtracking line search on |F| (stand-in for SNES line search "cp", elasticity.c:595-601):
             # full step first, halve while the residual norm does not decrease
             lam, taken = 1.0, 0.0

@@ -214,21 +214,34 @@ int b200_apply_diagonal(int problem, const b200_physics *phys, int nelem, int P,
 
 /* ---- halo exchange over NVLink peer memory (one node, one process per GPU; the DMLocalToGlobal(ADD) +
  * DMGlobalToLocal(INSERT) pair of matops.c:33,57 as one symmetric sum-and-share, no communication library on the
- * data path).  Each rank owns a window [parity 0 | parity 1] of packed shared dofs plus one int64 flag per neighbour,
- * allocated with b200_malloc and exported with CUDA IPC; neighbours store their partial sums into it.
- *   b200_halo_push_signal: packed position i of segment s (seg_start[s] <= i < seg_start[s+1]) is stored to
- *                          remote[s][i - seg_start[s]] (peer pointer for this generation's parity), then
- *                          *remote_flag[s] = gen (release, system scope);
- *   b200_halo_wait_unpack: waits until d_flags[0..nnbr) >= gen (bounded by timeout_s; on expiry *d_err = 1 and the
- *                          kernel returns -- loud failure instead of a hung GPU), then y[idx[i]] += window[i]. */
+ * data path).  Each rank owns a window of b200_halo_window_bytes(total) bytes
+ *     [parity 0: total doubles | parity 1: total doubles | one int64 flag per neighbour | generation | error word]
+ * allocated with b200_malloc (zeroed) and exported with CUDA IPC; neighbours store their partial sums into it.
+ *   b200_halo_begin  (side stream, high priority, ordered behind everything queued on the compute stream): packed
+ *                    position i of segment s (seg_start[s] <= i < seg_start[s+1]) of d_y[d_idx[i]] is stored to
+ *                    remote_p{parity}[s][i - seg_start[s]], then *remote_flag[s] = generation (release, system scope);
+ *   b200_halo_end    (compute stream): waits until every neighbour's flag shows this generation (bounded by timeout_s;
+ *                    on expiry the error word is set and the kernel returns -- loud failure instead of a hung GPU), then
+ *                    for every unique shared dof u: y[udof[u]] = sum over uent[uptr[u] .. uptr[u+1]) in that order of
+ *                    (entry < 0 ? y[udof[u]] : window[entry]) -- the holders' partial sums in ascending rank order, so
+ *                    every holder computes the bit-identical total, without atomics.
+ * The caller may keep the compute stream busy between begin and end with work that does not touch shared dofs. */
 #define B200_HALO_MAX_NEIGHBOURS 32
+typedef struct b200_halo b200_halo;
 int b200_ipc_get_handle(const void *dptr, unsigned char *handle64);
 int b200_ipc_open(const unsigned char *handle64, void **dptr);
 int b200_ipc_close(void *dptr);
-int b200_halo_push_signal(int nnbr, const int *seg_start, double *const *remote, long long *const *remote_flag,
-                          const int *d_idx, const double *d_y, long long gen);
-int b200_halo_wait_unpack(int nnbr, const long long *d_flags, long long gen, const int *d_idx, const double *d_window,
-                          double *d_y, size_t total, int *d_err, double timeout_s);
+size_t b200_halo_window_bytes(size_t total);
+int b200_halo_create(int nnbr, const int *seg_start, double *const *remote_p0, double *const *remote_p1,
+                     long long *const *remote_flag, const int *d_idx, size_t total, void *d_window, int nuniq,
+                     const int *d_udof, const int *d_uptr, const int *d_uent, double timeout_s, b200_halo **out);
+int b200_halo_destroy(b200_halo *h);
+int b200_halo_begin(b200_halo *h, const double *d_y);
+int b200_halo_end(b200_halo *h, double *d_y);
+int b200_halo_error(b200_halo *h, int *err);   /* synchronises; *err != 0: an exchange timed out */
+/* the same ordered sum for exchanges carried by a communication library (d_recv laid out like a window) */
+int b200_halo_unpack_ordered(int nuniq, const int *d_udof, const int *d_uptr, const int *d_uent, const double *d_recv,
+                             double *d_y);
 
 /* FP64 pipe probe: sustained DFMA/s of the device (8 independent chains per thread), for the FP64 cross-check of the
  * HBM roofline; synchronises */

@@ -182,6 +182,10 @@ CEED_EXTERN int CeedOperatorDestroy(CeedOperator *op);
 /* 1 if the operator's Apply runs as ONE fused kernel (gather..scatter), 0 if generic */
 /* ApplyAdd on the element range [start, stop) of a fused operator (halo-exchange overlap in partitioned runs) */
 CEED_EXTERN int CeedOperatorApplyAddRangeB200(CeedOperator op, CeedVector in, CeedVector out, CeedInt start, CeedInt stop);
+/* the partitioned MatMult of ApplyLocalCeedOp (matops.c:26-60) in one call: interface elements, halo exchange
+ * (b200_halo handle, include/b200_kernels.h; NULL = none) overlapped with the interior elements, Dirichlet rows zeroed */
+CEED_EXTERN int CeedOperatorApplyPartitionedB200(CeedOperator op, CeedVector in, CeedVector out, CeedInt n_interface,
+                                                 void *halo, const CeedInt *d_mask, CeedInt nmask);
 /* fused p-multigrid transfer operators: apply the fine-side inverse-multiplicity scaling of Prolong_Ceed /
  * Restrict_Ceed (matops.c:149,176) inside the kernel; inject != 0: the prolongation stores the interpolant */
 CEED_EXTERN int CeedOperatorSetTransferScalingB200(CeedOperator op, CeedVector scale, int inject);

@@ -113,9 +113,15 @@ def test_partitioned_apply_matches_serial(tmp_path, world, n, p):
         assert d["mult"].min() >= 1
     assert np.all(seen == 1), "every dof must be owned by exactly one rank"
     holders = np.zeros(gmesh.lsize(p))
+    first_copy = np.full(gmesh.lsize(p), np.nan)
     for r in range(world):
         gd, ys, mult = np.load(tmp_path / f"shared{r}.npy")
         gd = gd.astype(np.int64)
+        # the sum-and-share adds the holders' partial sums in ascending rank order on every holder: the copies of an
+        # interface dof are BIT-IDENTICAL across ranks (consistent "shared" vectors, reproducible dot products)
+        seen_before = ~np.isnan(first_copy[gd])
+        assert np.array_equal(ys[seen_before], first_copy[gd][seen_before]), f"rank {r}: interface copies differ bitwise"
+        first_copy[gd] = ys
         # every copy on every rank carries the assembled value; rank_multiplicity counts the holders
         assert np.linalg.norm(ys - yser[gd]) < 1e-13 * np.linalg.norm(yser)
         np.add.at(holders, gd, 1.0 / mult)
