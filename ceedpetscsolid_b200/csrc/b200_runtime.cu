@@ -50,18 +50,25 @@ __global__ void k_copy_where(double *dst, const double *src, const int *idx, siz
   GRID_STRIDE(i, n) { const int j = idx[i]; if (j >= 0) dst[i] = src[j]; }
 }
 // BLAS-1 with DEVICE scalars (alpha = sign * num[0] / den[0]): lets a Krylov loop run without host syncs
+// num / den of two device-resident scalars of a sync-free Krylov loop.  When the iteration has converged exactly
+// (r = 0 -> rz = 0, p = 0, pAp = 0) or broken down, the quotient would be 0/0: the step is then 0, so x, r and p
+// freeze instead of turning into NaN (the loop looks at the residual only every few iterations).
+__device__ __forceinline__ double guarded_ratio(double num, double den) {
+  const double a = num / den;
+  return (den != 0.0 && isfinite(a)) ? a : 0.0;
+}
 __global__ void k_axpy_dev(double *y, const double *x, size_t n, const double *num, const double *den, double sign) {
-  const double a = sign * num[0] / den[0];
+  const double a = sign * guarded_ratio(num[0], den[0]);
   GRID_STRIDE(i, n) y[i] += a * x[i];
 }
 __global__ void k_aypx_dev(double *y, const double *x, size_t n, const double *num, const double *den) {
-  const double a = num[0] / den[0];
+  const double a = guarded_ratio(num[0], den[0]);
   GRID_STRIDE(i, n) y[i] = x[i] + a * y[i];
 }
 // CG update in one pass: x += alpha p, r -= alpha Ap, z = dinv .* r   (alpha = rz / pAp, device scalars)
 __global__ void k_pcg_update(double *x, double *r, double *z, const double *p, const double *Ap, const double *dinv,
                              size_t n, const double *rz, const double *pAp) {
-  const double a = rz[0] / pAp[0];
+  const double a = guarded_ratio(rz[0], pAp[0]);
   GRID_STRIDE(i, n) {
     if (x) x[i] += a * p[i];  // x == NULL: Lanczos run for eigenvalue estimates, the iterate is not needed
     const double ri = r[i] - a * Ap[i];

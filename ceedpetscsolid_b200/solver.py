@@ -151,6 +151,16 @@ def pcg(V, A, b, x, M=None, rtol=1e-10, atol=1e-50, maxit=10000, work=None, hist
     return maxit, "maxit", math.sqrt(abs(rz))
 
 
+def _guarded_ratio(num, den):
+    """num / den of two scalars of a sync-free Krylov loop; 0 when the iteration has converged exactly or broken down
+    (0/0), so the iterates freeze instead of turning into NaN (same rule as guarded_ratio in csrc/b200_runtime.cu)."""
+    num, den = float(num), float(den)
+    if den == 0.0:
+        return 0.0
+    a = num / den
+    return a if math.isfinite(a) else 0.0
+
+
 def jacobi_pcg_nosync(V, A, dinv, b, x, work, rtol, maxit, check_every=10):
     """Jacobi-preconditioned CG from a zero initial guess whose scalars (r.z, p.Ap) stay on the DEVICE:
     the loop enqueues kernels without waiting for them and looks at the residual norm only every
@@ -193,16 +203,16 @@ def jacobi_pcg_nosync(V, A, dinv, b, x, work, rtol, maxit, check_every=10):
                 b2(lib.b200_pcg_update(x.data_ptr(), r.data_ptr(), z.data_ptr(), p.data_ptr(), Ap.data_ptr(),
                                        dinv.data_ptr(), x.numel(), sc[cur:cur + 1].data_ptr(), sc[2:3].data_ptr()))
             else:
-                a = sc[cur] / sc[2]
-                x.add_(p, alpha=float(a))
-                r.add_(Ap, alpha=-float(a))
+                a = _guarded_ratio(sc[cur], sc[2])
+                x.add_(p, alpha=a)
+                r.add_(Ap, alpha=-a)
                 torch.mul(dinv, r, out=z)
             ddot(r, z, nxt)
             if p.is_cuda:
                 b2(lib.b200_vec_aypx_dev(p.data_ptr(), z.data_ptr(), p.numel(), sc[nxt:nxt + 1].data_ptr(),
                                          sc[cur:cur + 1].data_ptr()))
             else:
-                p.mul_(float(sc[nxt] / sc[cur])).add_(z)
+                p.mul_(_guarded_ratio(sc[nxt], sc[cur])).add_(z)
             cur, nxt = nxt, cur
             it += 1
         rn = math.sqrt(abs(float(sc[cur].item())))  # the only host sync of this block of iterations

@@ -34,4 +34,4 @@ def test_peer_memory_halo_matches_oracle(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, MGPU_SHARED="masked", MGPU_HALO="p2p"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "PASS" in r.stdout and "halo=p2p" in r.stdout
+    assert "PASS" in r.stdout and "halo p2p" in r.stdout and "bit-identical: True" in r.stdout

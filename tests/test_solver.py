@@ -236,3 +236,31 @@ def test_h_multigrid_coarse_solve_is_mesh_independent_on_the_oracle_operator():
     assert its[8][0] <= its[4][0] + 4, its          # multigrid: flat
     assert its[8][1] >= 1.5 * its[4][1], its        # Jacobi: grows like 1/h
     assert its[8][0] < its[8][1] / 3, its
+
+
+def test_sync_free_pcg_survives_exact_convergence_inside_a_check_block():
+    """A diagonal operator makes Jacobi-PCG exact after one iteration; the loop only looks at the residual every
+    check_every iterations, so the remaining iterations of the block run with r = 0 (rz = pAp = 0).  The step
+    lengths are guarded: the solution stays exact instead of turning into NaN (coarsest h-multigrid levels with a
+    single interior node hit exactly this)."""
+    V = solver.Vec()
+    d = torch.tensor([2.0, 2.0, 2.0], dtype=torch.float64)
+    A = lambda x, y: y.copy_(d * x)
+    b = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    x = torch.zeros(3, dtype=torch.float64)
+    work = [torch.zeros(3, dtype=torch.float64) for _ in range(4)]
+    its = solver.jacobi_pcg_nosync(V, A, 1.0 / d, b, x, work, rtol=1e-12, maxit=50)
+    assert its == 10
+    assert torch.equal(x, b / d)
+
+
+@pytest.mark.gpu
+def test_sync_free_pcg_survives_exact_convergence_on_the_device():
+    V = solver.Vec()
+    d = torch.tensor([2.0, 2.0, 2.0], dtype=torch.float64, device="cuda")
+    A = lambda x, y: y.copy_(d * x)
+    b = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device="cuda")
+    x = torch.zeros_like(b)
+    work = [torch.zeros_like(b) for _ in range(4)]
+    its = solver.jacobi_pcg_nosync(V, A, 1.0 / d, b, x, work, rtol=1e-12, maxit=50)
+    assert its == 10 and torch.equal(x, b / d)
