@@ -117,118 +117,124 @@ struct QFArgs {
 // Q-vectors are [elem][size][nq]; thread per (elem, q)
 struct QFCtx { double v[4]; };
 
+// one quadrature point (element e, point q) of a recognised QFunction.  __host__ __device__: the kernel below runs it
+// on the device; b200_qfunction_apply_host runs the SAME body on the host, which is how the backend checks at
+// operator set-up that the caller's own QFunction (the host pointer given to CeedQFunctionCreateInterior) computes
+// what this body computes.
+__host__ __device__ inline void qf_point(int qf, const Material &mt, const QFCtx &cx, int isize, int nq, const QFArgs &a,
+                                         size_t e, size_t q) {
+#define IN(k, sz, comp) a.in[k][(e * (sz) + (comp)) * nq + q]
+#define OUT(k, sz, comp) a.out[k][(e * (sz) + (comp)) * nq + q]
+  if (qf == B200_QF_IDENTITY) {
+    for (int c = 0; c < isize; c++) OUT(0, isize, c) = IN(0, isize, c);
+    return;
+  }
+  if (qf == B200_QF_SETUPGEO) {  // qfunctions/common.h:47-101
+    double J[3][3];            // J[c][d] = dx_c/dX_d = in0[d][c]
+    for (int d = 0; d < 3; d++)
+      for (int c = 0; c < 3; c++) J[c][d] = IN(0, 9, d * 3 + c);
+    double Ad[3][3];
+    Ad[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    Ad[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+    Ad[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+    Ad[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    Ad[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+    Ad[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+    Ad[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    Ad[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+    Ad[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double detJ = J[0][0] * Ad[0][0] + J[1][0] * Ad[0][1] + J[2][0] * Ad[0][2];
+    OUT(0, 10, 0) = IN(1, 1, 0) * detJ;
+    for (int r = 0; r < 3; r++)
+      for (int s = 0; s < 3; s++) OUT(0, 10, 1 + 3 * r + s) = Ad[r][s] / detJ;
+    return;
+  }
+  if (qf == B200_QF_CONST_FORCE) {  // qfunctions/constantForce.h:39-70: force = vector * w detJ
+    const double w = IN(1, 10, 0);
+    for (int c = 0; c < 3; c++) OUT(0, 3, c) = cx.v[c] * w;
+    return;
+  }
+  if (qf == B200_QF_MMS_FORCE || qf == B200_QF_MMS_TRUE) {
+    // manufactured solution u = (e^2x sin3y cos4z, e^3y sin4z cos2x, e^4z sin2x cos3y) / 1e8
+    // (qfunctions/manufacturedTrue.h:30-56); forcing f = -div sigma(u) for the reference's
+    // linear-elastic stress law (linElas.h:127-139, shear entries mu*e_ij) times w detJ
+    // (qfunctions/manufacturedForce.h:39-103), written from the closed-form second derivatives
+    const double x = IN(0, 3, 0), y = IN(0, 3, 1), z = IN(0, 3, 2);
+    const double ex = exp(2 * x), ey = exp(3 * y), ez = exp(4 * z);
+    const double s2x = sin(2 * x), c2x = cos(2 * x), s3y = sin(3 * y), c3y = cos(3 * y), s4z = sin(4 * z), c4z = cos(4 * z);
+    const double u1 = ex * s3y * c4z, u2 = ey * s4z * c2x, u3 = ez * s2x * c3y;
+    if (qf == B200_QF_MMS_TRUE) {
+      OUT(0, 3, 0) = u1 / 1e8; OUT(0, 3, 1) = u2 / 1e8; OUT(0, 3, 2) = u3 / 1e8;
+      return;
+    }
+    const double lam = mt.E * mt.nu / ((1 + mt.nu) * (1 - 2 * mt.nu)), mu = mt.mu;
+    const double u1xx = 4 * u1, u1yy = -9 * u1, u1zz = -16 * u1, u1xy = 6 * ex * c3y * c4z, u1xz = -8 * ex * s3y * s4z;
+    const double u2yy = 9 * u2, u2xx = -4 * u2, u2zz = -16 * u2, u2xy = -6 * ey * s4z * s2x, u2yz = 12 * ey * c4z * c2x;
+    const double u3zz = 16 * u3, u3xx = -4 * u3, u3yy = -9 * u3, u3xz = 8 * ez * c2x * c3y, u3yz = -12 * ez * s2x * s3y;
+    const double w = IN(1, 10, 0) / 1e8;
+    OUT(0, 3, 0) = -(lam * (u1xx + u2xy + u3xz) + 2 * mu * u1xx + 0.5 * mu * (u1yy + u2xy + u1zz + u3xz)) * w;
+    OUT(0, 3, 1) = -(lam * (u1xy + u2yy + u3yz) + 2 * mu * u2yy + 0.5 * mu * (u2xx + u1xy + u2zz + u3yz)) * w;
+    OUT(0, 3, 2) = -(lam * (u1xz + u2yz + u3zz) + 2 * mu * u3zz + 0.5 * mu * (u3xx + u1xz + u3yy + u2yz)) * w;
+    return;
+  }
+  if (qf >= B200_QF_LINELAS_ENERGY && qf <= B200_QF_HYPERFS_DIAG) {
+    // post-processing: energy (du, qdata) -> w psi;  diagnostic (u, du, qdata) -> u, p, I1, I2, J, psi
+    const bool diag = qf >= B200_QF_LINELAS_DIAG;
+    const int kd = diag ? 1 : 0, kq = diag ? 2 : 1;  // field index of du and of qdata
+    double H[3][3], A[3][3], p[5];
+    for (int d = 0; d < 3; d++)
+      for (int c = 0; c < 3; c++) H[c][d] = IN(kd, 9, d * 3 + c);
+    for (int r = 0; r < 3; r++)
+      for (int s = 0; s < 3; s++) A[r][s] = IN(kq, 10, 1 + 3 * r + s);
+    const int prob = (qf - (diag ? B200_QF_LINELAS_DIAG : B200_QF_LINELAS_ENERGY));
+    if (prob == 0) post_point<B200_PROB_LINELAS>(mt, A, H, p);
+    else if (prob == 1) post_point<B200_PROB_HYPERSS>(mt, A, H, p);
+    else post_point<B200_PROB_HYPERFS>(mt, A, H, p);
+    if (diag) {
+      for (int c = 0; c < 3; c++) OUT(0, 8, c) = IN(0, 3, c);
+      for (int c = 0; c < 5; c++) OUT(0, 8, 3 + c) = p[c];
+    } else {
+      OUT(0, 1, 0) = p[4] * IN(kq, 10, 0);
+    }
+    return;
+  }
+  // solid-mechanics point functions: in0 = du [d][c], in1 = qdata[10], (in2 = gradu [c][k])
+  double H[3][3], A[3][3], W[3][3], g[3][3];
+  for (int d = 0; d < 3; d++)
+    for (int c = 0; c < 3; c++) H[c][d] = IN(0, 9, d * 3 + c);
+  const double w = IN(1, 10, 0);
+  for (int r = 0; r < 3; r++)
+    for (int s = 0; s < 3; s++) A[r][s] = IN(1, 10, 1 + 3 * r + s);
+  bool store_g = false;
+  switch (qf) {
+    case B200_QF_LINELAS_F:
+    case B200_QF_LINELAS_DF: linelas_point(mt, w, A, H, W); break;
+    case B200_QF_HYPERSS_F: hyperss_f_point(mt, w, A, H, g, W); store_g = true; break;
+    case B200_QF_HYPERFS_F: hyperfs_f_point(mt, w, A, H, g, W); store_g = true; break;
+    case B200_QF_HYPERSS_DF: {
+      const double s = 1. / (1. + (IN(2, 9, 0) + IN(2, 9, 4) + IN(2, 9, 8)));
+      hyperss_df_point(mt, w, A, s, H, W);
+    } break;
+    case B200_QF_HYPERFS_DF: {
+      for (int c = 0; c < 3; c++)
+        for (int k = 0; k < 3; k++) g[c][k] = IN(2, 9, c * 3 + k);
+      hyperfs_df_point_faithful(mt, w, A, g, H, W);
+    } break;
+    default: return;
+  }
+  for (int k = 0; k < 3; k++)
+    for (int c = 0; c < 3; c++) OUT(0, 9, k * 3 + c) = W[c][k];
+  if (store_g)
+    for (int c = 0; c < 3; c++)
+      for (int k = 0; k < 3; k++) OUT(1, 9, c * 3 + k) = g[c][k];
+#undef IN
+#undef OUT
+}
+
 __global__ void k_qfunction(int qf, const __grid_constant__ Material mt, const __grid_constant__ QFCtx cx, int isize,
                             int nelem, int nq, const __grid_constant__ QFArgs a) {
   const size_t total = (size_t)nelem * nq;
-  GRID_STRIDE(i, total) {
-    const size_t e = i / nq, q = i % nq;
-#define IN(k, sz, comp) a.in[k][(e * (sz) + (comp)) * nq + q]
-#define OUT(k, sz, comp) a.out[k][(e * (sz) + (comp)) * nq + q]
-    if (qf == B200_QF_IDENTITY) {
-      for (int c = 0; c < isize; c++) OUT(0, isize, c) = IN(0, isize, c);
-      continue;
-    }
-    if (qf == B200_QF_SETUPGEO) {  // qfunctions/common.h:47-101
-      double J[3][3];            // J[c][d] = dx_c/dX_d = in0[d][c]
-      for (int d = 0; d < 3; d++)
-        for (int c = 0; c < 3; c++) J[c][d] = IN(0, 9, d * 3 + c);
-      double Ad[3][3];
-      Ad[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-      Ad[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
-      Ad[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
-      Ad[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
-      Ad[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
-      Ad[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
-      Ad[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-      Ad[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
-      Ad[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-      const double detJ = J[0][0] * Ad[0][0] + J[1][0] * Ad[0][1] + J[2][0] * Ad[0][2];
-      OUT(0, 10, 0) = IN(1, 1, 0) * detJ;
-      for (int r = 0; r < 3; r++)
-        for (int s = 0; s < 3; s++) OUT(0, 10, 1 + 3 * r + s) = Ad[r][s] / detJ;
-      continue;
-    }
-    if (qf == B200_QF_CONST_FORCE) {  // qfunctions/constantForce.h:39-70: force = vector * w detJ
-      const double w = IN(1, 10, 0);
-      for (int c = 0; c < 3; c++) OUT(0, 3, c) = cx.v[c] * w;
-      continue;
-    }
-    if (qf == B200_QF_MMS_FORCE || qf == B200_QF_MMS_TRUE) {
-      // manufactured solution u = (e^2x sin3y cos4z, e^3y sin4z cos2x, e^4z sin2x cos3y) / 1e8
-      // (qfunctions/manufacturedTrue.h:30-56); forcing f = -div sigma(u) for the reference's
-      // linear-elastic stress law (linElas.h:127-139, shear entries mu*e_ij) times w detJ
-      // (qfunctions/manufacturedForce.h:39-103), written from the closed-form second derivatives
-      const double x = IN(0, 3, 0), y = IN(0, 3, 1), z = IN(0, 3, 2);
-      const double ex = exp(2 * x), ey = exp(3 * y), ez = exp(4 * z);
-      const double s2x = sin(2 * x), c2x = cos(2 * x), s3y = sin(3 * y), c3y = cos(3 * y), s4z = sin(4 * z), c4z = cos(4 * z);
-      const double u1 = ex * s3y * c4z, u2 = ey * s4z * c2x, u3 = ez * s2x * c3y;
-      if (qf == B200_QF_MMS_TRUE) {
-        OUT(0, 3, 0) = u1 / 1e8; OUT(0, 3, 1) = u2 / 1e8; OUT(0, 3, 2) = u3 / 1e8;
-        continue;
-      }
-      const double lam = mt.E * mt.nu / ((1 + mt.nu) * (1 - 2 * mt.nu)), mu = mt.mu;
-      const double u1xx = 4 * u1, u1yy = -9 * u1, u1zz = -16 * u1, u1xy = 6 * ex * c3y * c4z, u1xz = -8 * ex * s3y * s4z;
-      const double u2yy = 9 * u2, u2xx = -4 * u2, u2zz = -16 * u2, u2xy = -6 * ey * s4z * s2x, u2yz = 12 * ey * c4z * c2x;
-      const double u3zz = 16 * u3, u3xx = -4 * u3, u3yy = -9 * u3, u3xz = 8 * ez * c2x * c3y, u3yz = -12 * ez * s2x * s3y;
-      const double w = IN(1, 10, 0) / 1e8;
-      OUT(0, 3, 0) = -(lam * (u1xx + u2xy + u3xz) + 2 * mu * u1xx + 0.5 * mu * (u1yy + u2xy + u1zz + u3xz)) * w;
-      OUT(0, 3, 1) = -(lam * (u1xy + u2yy + u3yz) + 2 * mu * u2yy + 0.5 * mu * (u2xx + u1xy + u2zz + u3yz)) * w;
-      OUT(0, 3, 2) = -(lam * (u1xz + u2yz + u3zz) + 2 * mu * u3zz + 0.5 * mu * (u3xx + u1xz + u3yy + u2yz)) * w;
-      continue;
-    }
-    if (qf >= B200_QF_LINELAS_ENERGY && qf <= B200_QF_HYPERFS_DIAG) {
-      // post-processing: energy (du, qdata) -> w psi;  diagnostic (u, du, qdata) -> u, p, I1, I2, J, psi
-      const bool diag = qf >= B200_QF_LINELAS_DIAG;
-      const int kd = diag ? 1 : 0, kq = diag ? 2 : 1;  // field index of du and of qdata
-      double H[3][3], A[3][3], p[5];
-      for (int d = 0; d < 3; d++)
-        for (int c = 0; c < 3; c++) H[c][d] = IN(kd, 9, d * 3 + c);
-      for (int r = 0; r < 3; r++)
-        for (int s = 0; s < 3; s++) A[r][s] = IN(kq, 10, 1 + 3 * r + s);
-      const int prob = (qf - (diag ? B200_QF_LINELAS_DIAG : B200_QF_LINELAS_ENERGY));
-      if (prob == 0) post_point<B200_PROB_LINELAS>(mt, A, H, p);
-      else if (prob == 1) post_point<B200_PROB_HYPERSS>(mt, A, H, p);
-      else post_point<B200_PROB_HYPERFS>(mt, A, H, p);
-      if (diag) {
-        for (int c = 0; c < 3; c++) OUT(0, 8, c) = IN(0, 3, c);
-        for (int c = 0; c < 5; c++) OUT(0, 8, 3 + c) = p[c];
-      } else {
-        OUT(0, 1, 0) = p[4] * IN(kq, 10, 0);
-      }
-      continue;
-    }
-    // solid-mechanics point functions: in0 = du [d][c], in1 = qdata[10], (in2 = gradu [c][k])
-    double H[3][3], A[3][3], W[3][3], g[3][3];
-    for (int d = 0; d < 3; d++)
-      for (int c = 0; c < 3; c++) H[c][d] = IN(0, 9, d * 3 + c);
-    const double w = IN(1, 10, 0);
-    for (int r = 0; r < 3; r++)
-      for (int s = 0; s < 3; s++) A[r][s] = IN(1, 10, 1 + 3 * r + s);
-    bool store_g = false;
-    switch (qf) {
-      case B200_QF_LINELAS_F:
-      case B200_QF_LINELAS_DF: linelas_point(mt, w, A, H, W); break;
-      case B200_QF_HYPERSS_F: hyperss_f_point(mt, w, A, H, g, W); store_g = true; break;
-      case B200_QF_HYPERFS_F: hyperfs_f_point(mt, w, A, H, g, W); store_g = true; break;
-      case B200_QF_HYPERSS_DF: {
-        const double s = 1. / (1. + (IN(2, 9, 0) + IN(2, 9, 4) + IN(2, 9, 8)));
-        hyperss_df_point(mt, w, A, s, H, W);
-      } break;
-      case B200_QF_HYPERFS_DF: {
-        for (int c = 0; c < 3; c++)
-          for (int k = 0; k < 3; k++) g[c][k] = IN(2, 9, c * 3 + k);
-        hyperfs_df_point_faithful(mt, w, A, g, H, W);
-      } break;
-      default: return;
-    }
-    for (int k = 0; k < 3; k++)
-      for (int c = 0; c < 3; c++) OUT(0, 9, k * 3 + c) = W[c][k];
-    if (store_g)
-      for (int c = 0; c < 3; c++)
-        for (int k = 0; k < 3; k++) OUT(1, 9, c * 3 + k) = g[c][k];
-#undef IN
-#undef OUT
-  }
+  GRID_STRIDE(i, total) qf_point(qf, mt, cx, isize, nq, a, i / nq, i % nq);
 }
 
 // ---- B.5 diagonal, generic path: one (din, cin) unit-input pass ------------------------
@@ -352,23 +358,43 @@ extern "C" int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double
   return 0;
 }
 
-extern "C" int b200_qfunction_apply(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
-                                    int nin, const double *const *d_in, int nout, double *const *d_out) {
+static int qf_args(int qf_id, const double *h_ctx, int nctx, int nin, const double *const *in, int nout,
+                   double *const *out, QFArgs &a, QFCtx &cx, Material &mt) {
   if (nin > 4 || nout > 4) return set_error_msg("b200_qfunction_apply: at most 4 input and 4 output fields");
   if (qf_id <= B200_QF_NONE || qf_id > B200_QF_LAST) return set_error_msg("b200_qfunction_apply: unknown QFunction id");
   const int need_in = (qf_id == B200_QF_IDENTITY || qf_id == B200_QF_MMS_TRUE) ? 1
                       : (qf_id == B200_QF_HYPERSS_DF || qf_id == B200_QF_HYPERFS_DF || qf_id >= B200_QF_LINELAS_DIAG) ? 3 : 2;
   const int need_out = (qf_id == B200_QF_HYPERSS_F || qf_id == B200_QF_HYPERFS_F) ? 2 : 1;
   if (nin < need_in || nout < need_out) return set_error_msg("b200_qfunction_apply: field count does not match the QFunction");
-  QFArgs a;
   memset(&a, 0, sizeof a);
-  for (int i = 0; i < nin; i++) a.in[i] = d_in[i];
-  for (int i = 0; i < nout; i++) a.out[i] = d_out[i];
-  QFCtx cx;
+  for (int i = 0; i < nin; i++) a.in[i] = in[i];
+  for (int i = 0; i < nout; i++) a.out[i] = out[i];
   for (int i = 0; i < 4; i++) cx.v[i] = (h_ctx && i < nctx) ? h_ctx[i] : 0.0;
   b200_physics ph = {0.3, 1.0};
   if (h_ctx && nctx >= 2) { ph.nu = h_ctx[0]; ph.E = h_ctx[1]; }
-  const Material mt = make_material(&ph);
+  mt = make_material(&ph);
+  return 0;
+}
+
+// the same point functions evaluated on the HOST (h_in / h_out are host Q-vectors [elem][size][nq]): used by the
+// backend to compare the caller's own QFunction with the device body on a few known points (no GPU work)
+extern "C" int b200_qfunction_apply_host(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
+                                         int nin, const double *const *h_in, int nout, double *const *h_out) {
+  QFArgs a;
+  QFCtx cx;
+  Material mt;
+  if (int rc = qf_args(qf_id, h_ctx, nctx, nin, h_in, nout, h_out, a, cx, mt)) return rc;
+  for (size_t e = 0; e < (size_t)nelem; e++)
+    for (size_t q = 0; q < (size_t)nq; q++) qf_point(qf_id, mt, cx, identity_size, nq, a, e, q);
+  return 0;
+}
+
+extern "C" int b200_qfunction_apply(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
+                                    int nin, const double *const *d_in, int nout, double *const *d_out) {
+  QFArgs a;
+  QFCtx cx;
+  Material mt;
+  if (int rc = qf_args(qf_id, h_ctx, nctx, nin, d_in, nout, d_out, a, cx, mt)) return rc;
   const size_t total = (size_t)nelem * nq;
   if (!total) return 0;
   k_qfunction<<<grid_for(total, 128), 128, 0, g_stream>>>(qf_id, mt, cx, identity_size, nelem, nq, a);

@@ -97,6 +97,7 @@ struct CeedQFunction_private {
   void *ctx;
   size_t ctxsize;
   int identity_size;
+  int guard_done;  /* the caller's host function has been compared with the device body (qf_guard) */
 };
 
 typedef struct {
@@ -854,6 +855,88 @@ static int is_qstrided(CeedElemRestriction r, int ncomp, int Q) {
 static int is_passive(CeedVector v) { return v && v != CEED_VECTOR_ACTIVE && v != CEED_VECTOR_NONE; }
 
 /* classify once all fields are set */
+/* The reference hands over a host function pointer AND a source locator (setuplibceed.c:370-372, 518-520, 818-820);
+ * this backend dispatches on the NAME in the locator to a hand-written device body and never executes the pointer on
+ * the data path.  A locally edited qfunctions header would then silently run the stock body -- so, once per QFunction,
+ * the caller's own function is run on the host on a few known points and compared with the device body evaluated on
+ * the host (b200_qfunction_apply_host: the same __host__ __device__ code).  A mismatch is a loud error.  Covers the
+ * hot-path QFunctions (SetupGeo, residual F and Jacobian dF of the three models); skipped when no host pointer was
+ * given (bindings without one) or CEED_B200_SKIP_QF_GUARD is set. */
+static int qf_guard(CeedQFunction qf) {
+  Ceed ceed = qf->ceed;
+  if (qf->guard_done || !qf->f || getenv("CEED_B200_SKIP_QF_GUARD")) return 0;
+  const int id = qf->qf_id;
+  if (id < B200_QF_SETUPGEO || id > B200_QF_HYPERFS_DF) return 0;
+  enum { NQ = 3 };
+  double hctx[2] = {0.3, 1.0};
+  if (id != B200_QF_SETUPGEO) {
+    if (!qf->ctx) return 0;  /* context not set yet: checked at the next set-up */
+    memcpy(hctx, qf->ctx, sizeof hctx);
+  }
+  /* known points: a mildly distorted geometry (J near diag(0.5, 0.4, 0.6)) and displacement gradients of a few % */
+  static const double Jref[NQ][9] = {{0.50, 0.02, -0.01, 0.03, 0.40, 0.02, -0.02, 0.01, 0.60},
+                                     {0.45, -0.03, 0.02, 0.01, 0.42, -0.02, 0.03, 0.02, 0.55},
+                                     {0.52, 0.01, 0.03, -0.02, 0.38, 0.01, 0.01, -0.03, 0.62}};
+  static const double wref[NQ] = {0.31, 0.17, 0.26};
+  static const double gref[NQ][9] = {{0.031, -0.012, 0.007, 0.015, -0.024, 0.011, -0.008, 0.019, 0.027},
+                                     {-0.022, 0.017, 0.013, -0.009, 0.033, -0.016, 0.021, -0.005, -0.014},
+                                     {0.012, 0.026, -0.019, 0.023, 0.008, 0.017, -0.011, -0.028, 0.035}};
+  double qdata[10 * NQ], in_buf[MAXF][10 * NQ], out_user[MAXF][10 * NQ], out_dev[MAXF][10 * NQ];
+  { /* qdata from the backend's own SetupGeo body */
+    double dx[9 * NQ], w[NQ];
+    for (int q = 0; q < NQ; q++) {
+      for (int k = 0; k < 9; k++) dx[k * NQ + q] = Jref[q][k];
+      w[q] = wref[q];
+    }
+    const double *gin[2] = {dx, w};
+    double *gout[1] = {qdata};
+    B2(ceed, b200_qfunction_apply_host(B200_QF_SETUPGEO, NULL, 0, 0, 1, NQ, 2, gin, 1, gout));
+  }
+  const double *in[MAXF];
+  double *outu[MAXF], *outd[MAXF];
+  for (int i = 0; i < qf->nin; i++) {
+    const QFField *f = &qf->in[i];
+    if (f->size > 10) return 0;
+    for (int q = 0; q < NQ; q++)
+      for (int k = 0; k < f->size; k++) {
+        double v;
+        if (f->size == 10) v = qdata[k * NQ + q];
+        else if (f->emode == CEED_EVAL_WEIGHT || f->size == 1) v = wref[q];
+        else if (id == B200_QF_SETUPGEO) v = Jref[q][k % 9];
+        else if (f->emode == CEED_EVAL_GRAD) v = gref[(q + 1) % NQ][k % 9] * 1.3;   /* du / deltadu */
+        else v = gref[q][k % 9];                                                  /* stored gradu */
+        in_buf[i][k * NQ + q] = v;
+      }
+    in[i] = in_buf[i];
+  }
+  for (int i = 0; i < qf->nout; i++) {
+    if (qf->out[i].size > 10) return 0;
+    memset(out_user[i], 0, sizeof out_user[i]);
+    memset(out_dev[i], 0, sizeof out_dev[i]);
+    outu[i] = out_user[i];
+    outd[i] = out_dev[i];
+  }
+  const int rc_user = qf->f(qf->ctx, NQ, in, outu);
+  if (rc_user) return CeedError(ceed, 1, "QFunction %s (%s): the caller's function returned %d on the known-answer points", qf->name, qf->source, rc_user);
+  B2(ceed, b200_qfunction_apply_host(id, hctx, id == B200_QF_SETUPGEO ? 0 : 2, 0, 1, NQ, qf->nin, in, qf->nout, outd));
+  for (int i = 0; i < qf->nout; i++) {
+    double scale = 0, diff = 0;
+    for (int k = 0; k < qf->out[i].size * NQ; k++) {
+      if (fabs(out_user[i][k]) > scale) scale = fabs(out_user[i][k]);
+      if (fabs(out_user[i][k] - out_dev[i][k]) > diff) diff = fabs(out_user[i][k] - out_dev[i][k]);
+    }
+    if (!(diff <= 1e-10 * (scale > 1e-300 ? scale : 1e-300)))
+      return CeedError(ceed, 1,
+                       "%s: the QFunction at %s does not compute what this backend's device body for \"%s\" computes "
+                       "(output \"%s\": max difference %.3e at scale %.3e on the known-answer points).  The backend runs its "
+                       "own hand-written body for the names it recognises and would silently ignore a modified source; "
+                       "there is no JIT of user headers and no CPU fallback.",
+                       CEED_B200_RESOURCE, qf->source, qf->name, qf->out[i].name, diff, scale);
+  }
+  qf->guard_done = 1;
+  return 0;
+}
+
 static int op_setup(CeedOperator op) {
   CeedQFunction qf = op->qf;
   for (int i = 0; i < qf->nin; i++)
@@ -864,6 +947,7 @@ static int op_setup(CeedOperator op) {
     return CeedError(op->ceed, 1,
                      "%s: QFunction \"%s\" (%s) is not one this backend has a device body for; there is no CPU fallback",
                      CEED_B200_RESOURCE, qf->name, qf->source);
+  CeedChk(qf_guard(qf));
   op->kind = OP_GENERIC;
   const int id = qf->qf_id;
   const int is_res = id == B200_QF_LINELAS_F || id == B200_QF_HYPERSS_F || id == B200_QF_HYPERFS_F;

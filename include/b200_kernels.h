@@ -161,6 +161,10 @@ int b200_basis_apply(int nelem, int ncomp, int P, int Q, const double *d_interp1
  * the 3-vector for the constant forcing; may be NULL when the QFunction takes none) */
 int b200_qfunction_apply(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
                          int nin, const double *const *d_in, int nout, double *const *d_out);
+/* the same point functions on the HOST (host Q-vectors, no GPU work): lets the backend compare the caller's own
+ * QFunction pointer (setuplibceed.c:370-372,518-520,818-820) with its device body on a few known points */
+int b200_qfunction_apply_host(int qf_id, const double *h_ctx, int nctx, int identity_size, int nelem, int nq,
+                              int nin, const double *const *h_in, int nout, double *const *h_out);
 
 /* generic-path piece of CeedOperatorLinearAssembleDiagonal (App. B.5): one unit-input pass,
  * ediag[e][cin][n] += sum_q sum_dout G_dout[q,n] dv[e][dout*3+cin][q] G_din[q,n]

@@ -2,8 +2,10 @@
  * SetupLibceedFineLevel / SetupLibceedLevel (/root/reference/src/setuplibceed.c:278-393,518-542,
  * 818-839) and ApplyLocalCeedOp (/root/reference/src/matops.c:40-50) for linear elasticity on a
  * 2x2x2 box of degree 2, written against <ceed.h> only.  A QFunction is declared with the
- * CEED_QFUNCTION macro exactly as the reference's qfunctions headers do (the backend dispatches on
- * the ":Name" locator; the host pointer is never called on the device path).
+ * CEED_QFUNCTION macro exactly as the reference's qfunctions headers do.  The backend dispatches on
+ * the ":Name" locator and, at operator set-up, runs the host pointer on a few known points to make sure
+ * it computes what its device body computes: the bodies here forward to the oracle's restated
+ * QFunctions (oracle/qf_port.c, test infrastructure), standing in for the reference's headers.
  * Exit code 0 and "capi_smoke OK" = operators built, applied, diagonal assembled, results finite. */
 #include <ceed.h>
 #include <math.h>
@@ -12,9 +14,12 @@
 
 typedef struct { CeedScalar nu, E; } Physics_s;
 
-CEED_QFUNCTION(SetupGeo)(void *ctx, CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) { return 1; }
-CEED_QFUNCTION(LinElasF)(void *ctx, CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) { return 1; }
-CEED_QFUNCTION(LinElasdF)(void *ctx, CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) { return 1; }
+int port_SetupGeo(void *ctx, int Q, const double *const *in, double *const *out);
+int port_LinElasF(void *ctx, int Q, const double *const *in, double *const *out);
+int port_LinElasdF(void *ctx, int Q, const double *const *in, double *const *out);
+CEED_QFUNCTION(SetupGeo)(void *ctx, CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) { return port_SetupGeo(ctx, Q, in, out); }
+CEED_QFUNCTION(LinElasF)(void *ctx, CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) { return port_LinElasF(ctx, Q, in, out); }
+CEED_QFUNCTION(LinElasdF)(void *ctx, CeedInt Q, const CeedScalar *const *in, CeedScalar *const *out) { return port_LinElasdF(ctx, Q, in, out); }
 
 static CeedInt *box_offsets(int n, int p, int ncomp) {
   const int P = p + 1, N = n * p + 1;

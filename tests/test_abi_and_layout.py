@@ -125,7 +125,9 @@ def _build_capi(tmp):
                     "-Wno-unused-parameter", "-Wno-unused-variable", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "c", "capi_smoke.c"), "-o", exe,
                     "-L" + os.path.join(ROOT, "ceedpetscsolid_b200"), "-lceed_b200",
-                    "-Wl,-rpath," + os.path.join(ROOT, "ceedpetscsolid_b200"), "-lm"], check=True)
+                    "-Wl,-rpath," + os.path.join(ROOT, "ceedpetscsolid_b200"),
+                    "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
+                    "-lm"], check=True)
     return exe
 
 
