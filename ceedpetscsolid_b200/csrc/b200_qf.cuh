@@ -49,12 +49,13 @@ B200_DI void linelas_point(const Material &mt, double w, const double (&A)[3][3]
 // ------------------------------------------------------------------ hyperSS
 // qfunctions/hyperSS.h:43-55
 B200_DI double log1p_series(double x) {
+  // odd reciprocals multiplied instead of divided (see log1p_series_in_y below)
   double y = x / (2. + x);
   const double y2 = y * y;
   double sum = y;
-  y *= y2; sum += y / 3;
-  y *= y2; sum += y / 5;
-  y *= y2; sum += y / 7;
+  y *= y2; sum += y * (1. / 3);
+  y *= y2; sum += y * (1. / 5);
+  y *= y2; sum += y * (1. / 7);
   return 2 * sum;
 }
 
@@ -88,24 +89,36 @@ B200_DI void hyperss_df_point(const Material &mt, double w, const double (&A)[3]
 
 // ------------------------------------------------------------------ hyperFS
 // qfunctions/hyperFS.h:45-67
-B200_DI double log1p_series_shifted(double x) {
+// range reduction of qfunctions/hyperFS.h:45-67: log1p(x) = shift + log1p(xr), xr in [1/sqrt2 - 1, sqrt2 - 1]
+B200_DI double log1p_shift(double x, double &xr) {
   const double left = 0.70710678118654752440 - 1, right = 1.41421356237309504880 - 1;
   const double half_ln2 = 0.34657359027997265471;
-  double sum = 0;
+  double shift = 0;
   if (x < left) {
-    sum -= half_ln2;
+    shift = -half_ln2;
     x = 1 + 2 * x;
   } else if (right < x) {
-    sum += half_ln2;
+    shift = half_ln2;
     x = (x - 1) / 2;
   }
-  double y = x / (2. + x);
+  xr = x;
+  return shift;
+}
+// the reference's series in y = x / (2 + x): 2 (y + y^3/3 + y^5/5 + y^7/7).  The odd reciprocals are multiplied
+// (the reference divides: differs by <= 1 ulp of a term that is itself < 2e-3 of the sum) -- an FP64 division costs
+// ~15 instructions on the device and there are three of them per quadrature point otherwise.
+B200_DI double log1p_series_in_y(double y) {
   const double y2 = y * y;
-  sum += y;
-  y *= y2; sum += y / 3;
-  y *= y2; sum += y / 5;
-  y *= y2; sum += y / 7;
+  double sum = y;
+  y *= y2; sum += y * (1. / 3);
+  y *= y2; sum += y * (1. / 5);
+  y *= y2; sum += y * (1. / 7);
   return 2 * sum;
+}
+B200_DI double log1p_series_shifted(double x) {
+  double xr;
+  const double shift = log1p_shift(x, xr);
+  return 2 * shift + log1p_series_in_y(xr / (2. + xr));
 }
 
 // 2E in Voigt order (00,11,22,12,02,01) and det(C) - 1 (hyperFS.h:72-80, :91-97)
@@ -181,10 +194,7 @@ B200_DI void hyperfs_f_point(const Material &mt, double w, const double (&A)[3][
     const int j = vj[m], k = vk[m];
     s[m] = g[j][k] + g[k][j] + g[j][0] * g[k][0] + g[j][1] * g[k][1] + g[j][2] * g[k][2];
   }
-  const double llnj = mt.lambda * log1p_series_shifted(det_sym_m1(s)) / 2.;
-  const double tv[6] = {mt.mu * s[0] + llnj, mt.mu * s[1] + llnj, mt.mu * s[2] + llnj, mt.mu * s[3], mt.mu * s[4], mt.mu * s[5]};
-  voigt_sym(tv, tau);
-  // F^-T = cof(F) / det F, scaled by w:  Kt[n][k] = w / detF * sum_m cof[n][m] A[k][m];   W = tau Kt
+  // cofactors of F first: det F shares ONE reciprocal with the series variable y = xr / (2 + xr)
   const double F00 = g[0][0] + 1., F11 = g[1][1] + 1., F22 = g[2][2] + 1.;
   double cof[3][3];
   cof[0][0] = F11 * F22 - g[1][2] * g[2][1];
@@ -196,7 +206,16 @@ B200_DI void hyperfs_f_point(const Material &mt, double w, const double (&A)[3][
   cof[2][0] = g[0][1] * g[1][2] - g[0][2] * F11;
   cof[2][1] = g[0][2] * g[1][0] - F00 * g[1][2];
   cof[2][2] = F00 * F11 - g[0][1] * g[1][0];
-  const double wr = w / (F00 * cof[0][0] + g[0][1] * cof[0][1] + g[0][2] * cof[0][2]);
+  const double detF = F00 * cof[0][0] + g[0][1] * cof[0][1] + g[0][2] * cof[0][2];
+  double xr;
+  const double shift = log1p_shift(det_sym_m1(s), xr);
+  const double den = 2. + xr;
+  const double rboth = 1. / (den * detF);
+  const double llnj = mt.lambda * (shift + 0.5 * log1p_series_in_y(xr * (rboth * detF)));
+  const double wr = w * (rboth * den);
+  const double tv[6] = {mt.mu * s[0] + llnj, mt.mu * s[1] + llnj, mt.mu * s[2] + llnj, mt.mu * s[3], mt.mu * s[4], mt.mu * s[5]};
+  voigt_sym(tv, tau);
+  // F^-T = cof(F) / det F, scaled by w:  Kt[n][k] = w / detF * sum_m cof[n][m] A[k][m];   W = tau Kt
   double Kt[3][3];
 #pragma unroll
   for (int n = 0; n < 3; n++)

@@ -181,8 +181,8 @@ class Elasticity:
             if world > 1:
                 from .halo import Halo
                 halo = Halo(self.gmesh, grid, rank, deg, dist)
-                if halo_mode == "p2p":
-                    halo.enable_p2p()
+                if halo_mode == "p2p" and not halo.enable_p2p():
+                    raise RuntimeError(f"peer-memory halo set-up failed: {halo._p2p_error}")
             dm = matops.LevelDM(self.mesh, deg, bc_faces=faces, halo=halo, device=f"cuda:{device_id}", shared=True,
                                 masked=masked)
             self.dms.append(dm)
@@ -219,8 +219,8 @@ class Elasticity:
             if coarse == "hmg" and getattr(self.gmesh, "structured", True) else None
         if halo_mode == "p2p":
             for dm in (h_dms or []):
-                if dm.halo is not None:
-                    dm.halo.enable_p2p()
+                if dm.halo is not None and not dm.halo.enable_p2p():
+                    raise RuntimeError(f"peer-memory halo set-up failed: {dm.halo._p2p_error}")
         for dm in self.dms + list(h_dms or []):
             if dm.dot_weight is not None:
                 self.V.weights[dm.nglobal] = dm.dot_weight

@@ -207,26 +207,79 @@ class Halo:
         object (csrc/b200_halo.cu).  Afterwards sum_and_share is push + signal on a high-priority side stream and
         wait + ordered unpack on the compute stream; `handle` can be given to CeedOperatorApplyPartitionedB200,
         which overlaps the exchange with the interior elements.  timeout_s (default $B200_HALO_TIMEOUT_S or 20):
-        how long a rank waits for a neighbour before it flags the exchange as failed (check_p2p raises)."""
-        import ctypes as C
+        how long a rank waits for a neighbour before it flags the exchange as failed (check_p2p raises).
+        Returns True when every rank succeeded; if any rank failed (no peer access, IPC refused ...) every rank
+        releases what it set up and returns False, and the exchange keeps going through torch.distributed."""
         import os
-        from .ceed import b2, lib
         dist = self.dist
         assert self.device.type == "cuda", "peer-memory halo needs CUDA tensors"
         if timeout_s is None:
             timeout_s = float(os.environ.get("B200_HALO_TIMEOUT_S", "20"))
+        import ctypes as C
+        from .ceed import b2, lib
+
+        def agree(err):
+            """collective: did any rank fail this phase?"""
+            flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                self._p2p_error = repr(err) if err is not None else "another rank could not set up its peer-memory window"
+                self._release_p2p_local()
+                return True
+            return False
+
+        # phase 1 (rank-local): allocate and export this rank's window
         total = int(self.share_cat.numel())
-        nbytes = int(lib.b200_halo_window_bytes(total))
-        buf = C.c_void_p()
-        b2(lib.b200_malloc(C.byref(buf), nbytes))
-        b2(lib.b200_memset(buf, 0, nbytes))
-        b2(lib.b200_sync())
-        handle = (C.c_ubyte * 64)()
-        b2(lib.b200_ipc_get_handle(buf, handle))
+        err, handle = None, (C.c_ubyte * 64)()
+        try:
+            nbytes = int(lib.b200_halo_window_bytes(total))
+            buf = C.c_void_p()
+            b2(lib.b200_malloc(C.byref(buf), nbytes))
+            self._p2p_buf = buf
+            b2(lib.b200_memset(buf, 0, nbytes))
+            b2(lib.b200_sync())
+            b2(lib.b200_ipc_get_handle(buf, handle))
+        except Exception as exc:
+            err = exc
+        if agree(err):
+            return False
+        # phase 2 (collective): everybody's handle and segment layout
         mine = {"rank": self.rank, "handle": bytes(handle), "total": total, "neighbours": list(self.neighbours),
                 "views": {r: self.share_views[r] for r in self.neighbours}}
         infos = [None] * dist.get_world_size()
         dist.all_gather_object(infos, mine)
+        # phase 3 (rank-local): map the neighbours' windows, create the exchange object
+        try:
+            self._map_neighbours(infos, total, timeout_s)
+        except Exception as exc:
+            err = exc
+        if agree(err):
+            return False
+        dist.barrier()   # every window is mapped before anyone pushes
+        return True
+
+    def _release_p2p_local(self, barrier=None):
+        """rank-local teardown (no collectives unless `barrier` is given: it is called between unmapping the
+        neighbours' windows and freeing the own one, so that nobody frees memory a neighbour still has mapped)"""
+        from .ceed import lib
+        p = getattr(self, "_p2p", None)
+        if p is not None and p.get("handle") is not None:
+            lib.b200_halo_destroy(p["handle"])
+        for base in getattr(self, "_p2p_open", []):
+            lib.b200_ipc_close(base)
+        self._p2p_open = []
+        if barrier is not None:
+            barrier()
+        buf = getattr(self, "_p2p_buf", None)
+        if buf is not None:
+            lib.b200_sync()
+            lib.b200_free(buf)
+        self._p2p, self._p2p_buf = None, None
+
+    def _map_neighbours(self, infos, total, timeout_s):
+        import ctypes as C
+        from .ceed import b2, lib
+        buf = self._p2p_buf
         nn = len(self.neighbours)
         seg_start = (C.c_int * (nn + 1))()
         remote = [(C.c_void_p * max(nn, 1))(), (C.c_void_p * max(nn, 1))()]   # per parity
@@ -249,7 +302,6 @@ class Halo:
                                 self.udof.numel(), self.udof.data_ptr(), self.uptr.data_ptr(), self.uent.data_ptr(),
                                 float(timeout_s), C.byref(h)))
         self._p2p = dict(buf=buf, handle=h)
-        dist.barrier()   # every window is mapped before anyone pushes
 
     @property
     def handle(self):
@@ -269,20 +321,26 @@ class Halo:
             raise RuntimeError("peer-memory halo exchange timed out waiting for a neighbour: the vectors it produced "
                                "are incomplete")
 
+    def p2p_failed_anywhere(self):
+        """Collective: True if a peer-memory exchange timed out on ANY rank (synchronises)."""
+        if getattr(self, "_p2p", None) is None:
+            return False
+        import ctypes as C
+        from .ceed import b2, lib
+        e = C.c_int(0)
+        b2(lib.b200_halo_error(self._p2p["handle"], C.byref(e)))
+        flag = torch.tensor([1 if e.value else 0], dtype=torch.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX)
+        return bool(int(flag.item()))
+
     def close(self):
         """Collective: unmap the neighbours' windows and free this rank's (after every rank is done with them)."""
-        p = getattr(self, "_p2p", None)
-        if p is None:
+        if getattr(self, "_p2p", None) is None:
             return
         from .ceed import b2, lib
         b2(lib.b200_sync())
         self.dist.barrier()
-        b2(lib.b200_halo_destroy(p["handle"]))
-        for base in self._p2p_open:
-            b2(lib.b200_ipc_close(base))
-        self.dist.barrier()
-        b2(lib.b200_free(p["buf"]))
-        self._p2p, self._p2p_open = None, []
+        self._release_p2p_local(barrier=self.dist.barrier)
 
     def _sum_and_share_p2p(self, Yloc):
         from .ceed import b2, lib

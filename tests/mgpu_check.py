@@ -40,8 +40,8 @@ def partitioned_parity(rank, world, local, layout="masked", halo_mode="p2p", pro
     halo = None
     if world > 1:
         halo = Halo(gmesh, grid, rank, p, dist)
-        if halo_mode == "p2p":
-            halo.enable_p2p()
+        if halo_mode == "p2p" and not halo.enable_p2p():
+            return float("nan"), False, False, f"peer-memory halo could not be set up: {halo._p2p_error}"
     dm = matops.LevelDM(mesh, p, bc_faces="all", halo=halo, shared=shared, masked=masked)
     user = matops.setup_jacobian_ctx(dm, ceed, data[fine], phys)
     user.overlap = overlap
@@ -71,9 +71,10 @@ def partitioned_parity(rank, world, local, layout="masked", halo_mode="p2p", pro
     for _ in range(repeats):   # several exchanges: generation counter and window parity
         matops.ApplyJacobian_Ceed(user, X, Y)
     torch.cuda.synchronize()
-    if halo is not None:
-        halo.check_p2p()
     matops.OVERLAP_MIN_INTERIOR = old_min
+    if halo is not None and halo.p2p_failed_anywhere():
+        halo.close()
+        return float("nan"), False, False, "a peer-memory halo exchange timed out waiting for a neighbour"
     # gather (dof id, value) pairs on rank 0
     parts = [(mydofs, Y.cpu().numpy())]
     if world > 1:
