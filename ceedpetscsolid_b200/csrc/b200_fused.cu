@@ -54,18 +54,13 @@ template <int Q> struct Cfg {
 
 #define IDX(c, x, y, z) ((c) * SC + (z) * SZ + (y) * SY + (x))
 
-// Component stride of the fused apply kernels.  The line stages never mix components, so the stride between
-// component lattices is free: for P = Q = 5 a pad of 14 doubles makes the final scatter sweep (lanes run over
-// (node, component) with the component fastest) bank-conflict free as well (97 wavefronts per CTA where 94 is
-// ideal, 188 unpadded; tools/smem_pad.py, checked in tests/test_abi_and_layout.py).  No pad helps the other pairs.
+// Shared-memory extents of the fused apply kernels: three gradient lattices of three components each.
+// (A padded component stride that made the final scatter sweep conflict-free was measured SLOWER, 1.26 vs 1.13 ms at
+// P = Q = 5: 42 kB per CTA pushes five resident CTAs past the 196 kB shared-memory carve-out and leaves the gather
+// 28 kB of L1 instead of 60 kB.  The sweep is made conflict-free without extra memory instead: the last stage writes
+// its nodal output interlaced, [node][component], into the lattices that are free by then.)
 __host__ __device__ constexpr int odd_extent(int Q) { return (Q % 2) ? Q : Q + 1; }
-__host__ __device__ constexpr int apply_sc(int P, int Q) {
-#ifdef B200_NO_SCPAD
-  return odd_extent(Q) * odd_extent(Q) * odd_extent(Q);
-#else
-  return odd_extent(Q) * odd_extent(Q) * odd_extent(Q) + ((P == 5 && Q == 5) ? 14 : 0);
-#endif
-}
+__host__ __device__ constexpr int apply_sc(int P, int Q) { return odd_extent(Q) * odd_extent(Q) * odd_extent(Q); }
 __host__ __device__ constexpr int apply_se(int Q, int SC) {
   return elems_per_block(Q) == 16 ? ((9 * SC) | 1) : 9 * SC + ((16 / elems_per_block(Q) - (9 * SC) % 16) + 16) % 16;
 }
@@ -333,8 +328,12 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
     }
   }
   __syncthreads();
-  // ---- phase 10: x-lines (a = j < P, b = k < P): B^T along x -> R0 (free since phase 8)
+  // ---- phase 10: x-lines (a = j < P, b = k < P): B^T along x -> nodal output, interlaced [node][component] at the
+  // start of the element's region (lattices R0 and R1 are free: last read in phases 8 and 9): the scatter sweep
+  // below then reads consecutive shared-memory words (no bank conflicts) in exactly L-vector order
   if (act && a < P && b < P) {
+    double *Rn = R0 + ((b * P + a) * P) * 3;
+    static_assert(3 * P3 <= 6 * SC, "interlaced nodal output must fit in the first two lattices");
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       double in[Q];
@@ -345,7 +344,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
         double s = 0;
 #pragma unroll
         for (int qx = 0; qx < Q; qx++) s += m.B[qx * P + i] * in[qx];
-        R0[IDX(c, i, a, b)] = s;
+        Rn[i * 3 + c] = s;
       }
     }
   }
@@ -752,7 +751,7 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
   if (int rc = cached_mats<P, Q>(hB, hD, m)) return rc;
   auto kern = k_fused_apply<P, Q, PROB, MODE, true>;
   auto kern_tail = k_fused_apply<P, Q, PROB, MODE, false>;
-  constexpr int EB = Cfg<Q>::EB, P3 = P * P * P, SZ = Cfg<Q>::SZ, SY = Cfg<Q>::SY, SC = apply_sc(P, Q), SE = apply_se(Q, SC);
+  constexpr int EB = Cfg<Q>::EB, P3 = P * P * P, SC = apply_sc(P, Q), SE = apply_se(Q, SC);
   constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10, Q3 = Q * Q * Q;
   const size_t smem_bytes = sizeof(double) * EB * SE + sizeof(int) * EB * P3;
   static PerDevice pd;
@@ -761,14 +760,13 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
   if (!pd.configured[dev]) {
     if (int rc = opt_in_smem(kern, smem_bytes)) return rc;
     if (int rc = opt_in_smem(kern_tail, smem_bytes)) return rc;
-    // scatter table: f = (el, node, c) with c fastest -> lattice index | offset index << 16 | c << 28
+    // scatter table: f = (el, node, c) with c fastest -> shared-memory word | offset index << 16 | c << 28
     static_assert(EB * SE < 65536 && EB * P3 < 4096, "scatter table packing");
     unsigned h[EB * P3 * 3];
     for (int el = 0; el < EB; el++)
       for (int node = 0; node < P3; node++)
         for (int c = 0; c < 3; c++) {
-          const int i = node % P, j = (node / P) % P, k = node / (P * P);
-          h[(el * P3 + node) * 3 + c] = (unsigned)(el * SE + IDX(c, i, j, k)) | ((unsigned)(el * P3 + node) << 16) | ((unsigned)c << 28);
+          h[(el * P3 + node) * 3 + c] = (unsigned)(el * SE + node * 3 + c) | ((unsigned)(el * P3 + node) << 16) | ((unsigned)c << 28);
         }
     B200_CHECK(cudaMalloc(&pd.table[dev], sizeof h));
     B200_CHECK(cudaMemcpy(pd.table[dev], h, sizeof h, cudaMemcpyHostToDevice));
