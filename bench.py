@@ -21,9 +21,20 @@ import sys
 import threading
 import time
 
-# the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on STDOUT: keep stdout = one JSON line
+# stdout must carry exactly ONE JSON line.  Libraries write banners to the C-level stdout (NCCL prints its version
+# there at NCCL_DEBUG=VERSION, which the image exports, and at WARN): file descriptor 1 is pointed at stderr for the
+# whole run and the result line is written to the saved descriptor.
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -195,7 +206,7 @@ def solve_bench(args, rank, world, local_rank, dist, config):
                 "warmup": 0, "ms_per_step": rec["time_s"] * 1e3, "higher_is_better": False,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config}
         line.update({k: v for k, v in rec.items() if k not in ("time_s", "workload", "scaling", "bricks", "elements_per_gpu")})
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -361,7 +372,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "omp_threads": cb["omp_threads"], "host_cpus": cb["host_cpus"]}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ /gpu/b200 arm
@@ -579,7 +590,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "parity": parity}
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

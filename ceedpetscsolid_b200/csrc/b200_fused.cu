@@ -72,6 +72,19 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, unsigned bytes) 
   if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// per-point stream: read once, never reused.  Default: ld.global.cs (evict-first in L1 and L2).
+// B200_STREAM_NOALLOC (tuning build): do not allocate the line in L1 at all -- keeps the small L1
+// (60 kB beside 196 kB of shared memory) for the gather of x and the offsets.
+__device__ __forceinline__ double ld_stream(const double *p) {
+#ifdef B200_STREAM_NOALLOC
+  double v;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldcs(p);
+#endif
+}
+
 enum { MODE_RESIDUAL = 0, MODE_JACOBIAN = 1 };
 
 // FULL: every CTA of the launch owns a complete group of EB elements, so the plane stride of the q-blocked
@@ -183,7 +196,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   if (act) {
     if (AHEAD) {
 #pragma unroll
-      for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q) * ebt);
+      for (int n = 0; n < NC; n++) qn[n] = ld_stream(qlane + (size_t)(n * Q) * ebt);
     }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -220,11 +233,11 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
         for (int n = 0; n < NC; n++) qd[n] = qn[n];
         if (qx + 1 < Q) {
 #pragma unroll
-          for (int n = 0; n < NC; n++) qn[n] = __ldcs(qlane + (size_t)(n * Q + qx + 1) * ebt);
+          for (int n = 0; n < NC; n++) qn[n] = ld_stream(qlane + (size_t)(n * Q + qx + 1) * ebt);
         }
       } else {
 #pragma unroll
-        for (int n = 0; n < NC; n++) qd[n] = __ldcs(qlane + (size_t)(n * Q + qx) * ebt);
+        for (int n = 0; n < NC; n++) qd[n] = ld_stream(qlane + (size_t)(n * Q + qx) * ebt);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
