@@ -94,7 +94,16 @@ template <int P, int Q, int PROB, int MODE, bool FULL>
 // min CTAs/SM: 5 x 128 threads caps the Jacobian kernels at 96 registers (no spills at P=Q=5) and
 // measured 3.5 % faster than 4 x 128 regs; the residual kernels keep all registers
 // (residual kernels: 4 CTAs/SM (128 registers, a few spilled words) measured 20 % faster than 1-2 CTAs at 228 registers)
-__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? 5 : 2) : (Cfg<Q>::NT <= 128 ? 4 : 1))
+#ifndef B200_JAC_CTAS
+#define B200_JAC_CTAS 5
+#endif
+#ifndef B200_RES_CTAS
+#define B200_RES_CTAS 4
+#endif
+#ifndef B200_RES_AHEAD
+#define B200_RES_AHEAD 0
+#endif
+__global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? B200_JAC_CTAS : 2) : (Cfg<Q>::NT <= 128 ? B200_RES_CTAS : 1))
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y,
@@ -191,7 +200,7 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   // ---- phase 3: y-lines (a = qx, b = qz): d/dy -> R1;  phase 4: z-lines (a = qx, b = qy): d/dz -> R2
   // per-point data of the NEXT quadrature point: loads stay in flight under the math (Jacobian kernels; the
   // hyperFS residual needs the registers for its point function and loads each point where it is used)
-  constexpr bool AHEAD = !(MODE == MODE_RESIDUAL && PROB == B200_PROB_HYPERFS);
+  constexpr bool AHEAD = B200_RES_AHEAD || !(MODE == MODE_RESIDUAL && PROB == B200_PROB_HYPERFS);
   double qn[NC];
   if (act) {
     if (AHEAD) {
@@ -451,7 +460,10 @@ template <int P, int Q> struct DiagMats {
 };
 
 template <int P, int Q, int PROB>
-__global__ void __launch_bounds__(Cfg<Q>::NT, 384 / Cfg<Q>::NT)
+#ifndef B200_DIAG_THREADS
+#define B200_DIAG_THREADS 384
+#endif
+__global__ void __launch_bounds__(Cfg<Q>::NT, B200_DIAG_THREADS / Cfg<Q>::NT)
 k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ Material mt, int nelem,
              const int *__restrict__ offsets, const double *__restrict__ jcp, double *__restrict__ diag,
              double *__restrict__ evec) {
