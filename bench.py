@@ -563,12 +563,14 @@ def main():
         xs.normal_()
         xcs, ycs = ps.data[ps.fine].xceed, ps.data[ps.fine].yceed
         xcs.set_array(xs); ycs.set_array(ys)
-        ks = timed(lambda: ps.data[ps.fine].opJacob.apply_add(xcs, ycs), 10, 3, world, dist) / 10
+        ks = min(timed(lambda: ps.data[ps.fine].opJacob.apply_add(xcs, ycs), 10, 3, world, dist) / 10 for _ in range(2))
         xcs.take_array(); ycs.take_array()
         extra["strong_c4"] = {"value": sd * args.steps / (mss * 1e-3) / 1e9, "unit": "GDoF/s", "ms_per_step": mss / args.steps,
                               "scaling": "strong", "dofs": sd, "elements_per_gpu": ps.mesh.nelem, "bricks": "x".join(map(str, ps.grid)),
                               "interface_elements": int(ps.mesh.n_interface), "kernel_ms_whole_brick": ks,
-                              "exposed_ms_per_step": mss / args.steps - ks,
+                              "exposed_ms_per_step": max(mss / args.steps - ks, 0.0),
+                              "exposed_what": "step minus the fused kernel over the whole brick timed separately (zeroing of Y, Dirichlet "
+                                              "mask, launches, halo exchange not hidden); the two timings see slightly different clocks",
                               "workload": f"{problem} degree {p} Jacobian MatMult, box {args.strong_box}^3 ({sd} DoFs) sharded over {world} GPU(s)"}
         ps.close()
         del ps, xs, ys, xcs, ycs

@@ -129,6 +129,7 @@ _proto("b200_vec_aypx", _vp, _d, _vp, _sz)
 _proto("b200_vec_axpby", _vp, _d, _vp, _d, _vp, _sz)
 _proto("b200_vec_pointwise_mult", _vp, _vp, _vp, _sz)
 _proto("b200_vec_dot", _vp, _vp, _sz, _vp)
+_proto("b200_vec_dot_weighted", _vp, _vp, _vp, _sz, _vp)
 _proto("b200_vec_dot_host", _vp, _vp, _sz, C.POINTER(_d))
 _proto("b200_vec_norm_host", _vp, _sz, _i, C.POINTER(_d))
 _proto("b200_gather", _vp, _vp, _vp, _sz)

@@ -101,7 +101,7 @@ template <int P, int Q, int PROB, int MODE, bool FULL>
 #define B200_RES_CTAS 4
 #endif
 #ifndef B200_RES_AHEAD
-#define B200_RES_AHEAD 0
+#define B200_RES_AHEAD 1
 #endif
 __global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? B200_JAC_CTAS : 2) : (Cfg<Q>::NT <= 128 ? B200_RES_CTAS : 1))
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
@@ -198,8 +198,9 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   }
   __syncthreads();
   // ---- phase 3: y-lines (a = qx, b = qz): d/dy -> R1;  phase 4: z-lines (a = qx, b = qy): d/dz -> R2
-  // per-point data of the NEXT quadrature point: loads stay in flight under the math (Jacobian kernels; the
-  // hyperFS residual needs the registers for its point function and loads each point where it is used)
+  // per-point data of the NEXT quadrature point: loads stay in flight under the math.  (A/B at 64^3, hyperFS residual,
+  // 4 CTAs/SM at 128 registers: look-ahead with 40 B of spills 1.44 ms, no look-ahead and no spills 1.52 ms, 3 CTAs/SM at
+  // 158 registers with look-ahead 1.53 ms: B200_RES_AHEAD / B200_RES_CTAS.)
   constexpr bool AHEAD = B200_RES_AHEAD || !(MODE == MODE_RESIDUAL && PROB == B200_PROB_HYPERFS);
   double qn[NC];
   if (act) {

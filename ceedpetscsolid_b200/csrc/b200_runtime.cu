@@ -188,13 +188,15 @@ __global__ void k_fill_strided(double *d, double v, size_t n, size_t stride, siz
 }
 __global__ void k_mask_zero(double *d, const int *idx, size_t n) { GRID_STRIDE(i, n) d[idx[i]] = 0.0; }
 
-// deterministic two-pass reductions (fixed grid, fixed tree): mode 0 dot, 1 sum|x|, 2 max|x|
+// deterministic two-pass reductions (fixed grid, fixed tree): mode 0 dot, 1 sum|x|, 2 max|x|, 3 weighted dot
+// sum_i w_i x_i y_i (shared-dof layouts count every dof once: w = 1 / number of ranks holding it)
 template <int MODE>
-__global__ void k_reduce_partial(const double *x, const double *y, size_t n, double *partial) {
+__global__ void k_reduce_partial(const double *x, const double *y, size_t n, double *partial, const double *w = nullptr) {
   __shared__ double sh[256];
   double s = 0;
   GRID_STRIDE(i, n) {
     if (MODE == 0) s += x[i] * y[i];
+    else if (MODE == 3) s += (w[i] * x[i]) * y[i];
     else if (MODE == 1) s += fabs(x[i]);
     else s = fmax(s, fabs(x[i]));
   }
@@ -220,13 +222,23 @@ __global__ void k_reduce_final(const double *partial, int np, double *out) {
   if (threadIdx.x == 0) *out = sh[0];
 }
 
-static double *g_partial = nullptr;  // 1024 partials + 1 result
+static double *g_partials[64] = {};  // per device: 1024 partials + 1 result
 static const int kReduceBlocks = 592;  // 148 SMs x 4
 
+static int partial_buffer(double **p) {
+  int dev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return set_error_msg("device ordinal out of range");
+  if (!g_partials[dev]) B200_CHECK(cudaMalloc(&g_partials[dev], sizeof(double) * 1032));
+  *p = g_partials[dev];
+  return 0;
+}
+
 template <int MODE>
-static int reduce(const double *x, const double *y, size_t n, double *dresult) {
-  if (!g_partial) B200_CHECK(cudaMalloc(&g_partial, sizeof(double) * 1032));
-  k_reduce_partial<MODE><<<kReduceBlocks, 256, 0, g_stream>>>(x, y, n, g_partial);
+static int reduce(const double *x, const double *y, size_t n, double *dresult, const double *w = nullptr) {
+  double *g_partial;
+  if (int rc = partial_buffer(&g_partial)) return rc;
+  k_reduce_partial<MODE><<<kReduceBlocks, 256, 0, g_stream>>>(x, y, n, g_partial, w);
   B200_LAUNCH_CHECK("k_reduce_partial");
   k_reduce_final<MODE><<<1, 256, 0, g_stream>>>(g_partial, kReduceBlocks, dresult);
   B200_LAUNCH_CHECK("k_reduce_final");
@@ -234,7 +246,8 @@ static int reduce(const double *x, const double *y, size_t n, double *dresult) {
 }
 template <int MODE>
 static int reduce_host(const double *x, const double *y, size_t n, double *hresult) {
-  if (!g_partial) B200_CHECK(cudaMalloc(&g_partial, sizeof(double) * 1032));
+  double *g_partial;
+  if (int rc = partial_buffer(&g_partial)) return rc;
   if (int rc = reduce<MODE>(x, y, n, g_partial + 1024)) return rc;
   B200_CHECK(cudaMemcpyAsync(hresult, g_partial + 1024, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   B200_CHECK(cudaStreamSynchronize(g_stream));
@@ -319,6 +332,9 @@ int b200_vec_pointwise_mult(double *w, const double *x, const double *y, size_t 
   VEC_KERNEL((k_pmult<<<grid_for(n, 256), 256, 0, g_stream>>>(w, x, y, n)), n);
 }
 int b200_vec_dot(const double *x, const double *y, size_t n, double *dresult) { return reduce<0>(x, y, n, dresult); }
+int b200_vec_dot_weighted(const double *w, const double *x, const double *y, size_t n, double *dresult) {
+  return reduce<3>(x, y, n, dresult, w);
+}
 int b200_vec_dot_host(const double *x, const double *y, size_t n, double *hresult) { return reduce_host<0>(x, y, n, hresult); }
 int b200_vec_norm_host(const double *x, size_t n, int norm_type, double *hresult) {
   int rc;

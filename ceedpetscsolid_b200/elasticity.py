@@ -223,7 +223,7 @@ class Elasticity:
                     raise RuntimeError(f"peer-memory halo set-up failed: {dm.halo._p2p_error}")
         for dm in self.dms + list(h_dms or []):
             if dm.dot_weight is not None:
-                self.V.weights[dm.nglobal] = dm.dot_weight
+                self.V.set_weight(dm.nglobal, dm.dot_weight)
             if dm.dot_weight is not None or dm.masked:
                 self.V.consistent[dm.nglobal] = dm.make_consistent
         self.all_dms = self.dms + list(h_dms or [])

@@ -39,6 +39,16 @@ class Vec:
         self.weights = {}   # vector length -> weight vector (shared-dof layouts count every dof once)
         self._wtmp = {}
 
+    def set_weight(self, n, w):
+        """Inner-product weight (1 / number of ranks holding the dof) for the vectors of length n.  The weights are
+        looked up by vector length: two DMs of the SAME length with DIFFERENT interface multiplicities cannot share one
+        Vec -- refused here instead of silently taking the last one registered."""
+        old = self.weights.get(int(n))
+        if old is not None and old is not w and not torch.equal(old, w):
+            raise ValueError(f"Vec.set_weight: two different dot-product weights for vectors of length {n}; "
+                             "give the second DM its own Vec")
+        self.weights[int(n)] = w
+
     def _weighted(self, a):
         w = self.weights.get(a.numel())
         if w is None:
@@ -50,14 +60,17 @@ class Vec:
         return t
 
     def dot(self, a, b):
-        a = self._weighted(a)
         if a.is_cuda:
             if self._scratch is None:
                 self._scratch = torch.zeros(1, dtype=torch.float64, device=a.device)
-            b2(lib.b200_vec_dot(a.data_ptr(), b.data_ptr(), a.numel(), self._scratch.data_ptr()))
+            w = self.weights.get(a.numel())
+            if w is None:
+                b2(lib.b200_vec_dot(a.data_ptr(), b.data_ptr(), a.numel(), self._scratch.data_ptr()))
+            else:   # (w .* a) . b in one pass, same rounding as the separate product
+                b2(lib.b200_vec_dot_weighted(w.data_ptr(), a.data_ptr(), b.data_ptr(), a.numel(), self._scratch.data_ptr()))
             s = self._scratch
         else:
-            s = torch.dot(a, b).reshape(1)
+            s = torch.dot(self._weighted(a), b).reshape(1)
         if self.dist is not None and self.dist.get_world_size() > 1:
             s = s.clone()
             self.dist.all_reduce(s)
@@ -176,11 +189,14 @@ def jacobi_pcg_nosync(V, A, dinv, b, x, work, rtol, maxit, check_every=10):
 
     def ddot(a_, b_, slot):
         out = sc[slot:slot + 1]
-        a_ = V._weighted(a_)
         if a_.is_cuda:
-            b2(lib.b200_vec_dot(a_.data_ptr(), b_.data_ptr(), a_.numel(), out.data_ptr()))
+            w = V.weights.get(a_.numel())
+            if w is None:
+                b2(lib.b200_vec_dot(a_.data_ptr(), b_.data_ptr(), a_.numel(), out.data_ptr()))
+            else:
+                b2(lib.b200_vec_dot_weighted(w.data_ptr(), a_.data_ptr(), b_.data_ptr(), a_.numel(), out.data_ptr()))
         else:
-            out.copy_(torch.dot(a_, b_).reshape(1))
+            out.copy_(torch.dot(V._weighted(a_), b_).reshape(1))
         if multi:
             V.dist.all_reduce(out)
         return out

@@ -89,6 +89,7 @@ int b200_vec_aypx(double *y, double alpha, const double *x, size_t n);          
 int b200_vec_axpby(double *z, double a, const double *x, double b, const double *y, size_t n);
 int b200_vec_pointwise_mult(double *w, const double *x, const double *y, size_t n);
 int b200_vec_dot(const double *x, const double *y, size_t n, double *dresult);    /* device scalar */
+int b200_vec_dot_weighted(const double *w, const double *x, const double *y, size_t n, double *dresult); /* sum (w x) y */
 int b200_vec_dot_host(const double *x, const double *y, size_t n, double *hresult);
 int b200_vec_norm_host(const double *x, size_t n, int norm_type, double *hresult); /* 0=1,1=2,2=max */
 /* index gather / scatter used by the halo exchange and the global<->local maps

@@ -116,7 +116,7 @@ def oracle_solve(app, log=None, coarse="hmg", masked=True, dist=None, rank=0, wo
         if coarse == "hmg" and getattr(sh.gmesh, "structured", True) else None
     for dm in [lev.dm for lev in levels] + list(h_dms or []):
         if dm.dot_weight is not None:
-            V.weights[dm.nglobal] = dm.dot_weight
+            V.set_weight(dm.nglobal, dm.dot_weight)
         if dm.dot_weight is not None or dm.masked:
             V.consistent[dm.nglobal] = dm.make_consistent
     pc = solver.PMultigrid(V, levels, transfers, h_dms=h_dms)

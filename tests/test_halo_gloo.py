@@ -157,7 +157,7 @@ def _masked_worker(rank, world, port, n, p, out):
 
         V = solver.Vec(dist if world > 1 else None)
         if dm.dot_weight is not None:
-            V.weights[dm.nglobal] = dm.dot_weight
+            V.set_weight(dm.nglobal, dm.dot_weight)
         b = torch.from_numpy(np.random.default_rng(9).standard_normal(gmesh.lsize(p))[gdof].copy())
         dm.zero_constrained(b)
         x = torch.zeros_like(b)

@@ -264,3 +264,15 @@ def test_sync_free_pcg_survives_exact_convergence_on_the_device():
     work = [torch.zeros_like(b) for _ in range(4)]
     its = solver.jacobi_pcg_nosync(V, A, 1.0 / d, b, x, work, rtol=1e-12, maxit=50)
     assert its == 10 and torch.equal(x, b / d)
+
+
+def test_dot_product_weights_of_equal_length_must_agree():
+    """Vec looks inner-product weights up by vector length: registering a DIFFERENT weight for a length that already
+    has one is refused (it would silently change every dot product of the first DM)."""
+    V = solver.Vec()
+    w1 = torch.tensor([1.0, 0.5, 1.0])
+    V.set_weight(3, w1)
+    V.set_weight(3, w1.clone())                      # same values: fine
+    with pytest.raises(ValueError, match="different dot-product weights"):
+        V.set_weight(3, torch.tensor([1.0, 1.0, 0.5]))
+    assert V.dot(torch.ones(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)) == 2.5
