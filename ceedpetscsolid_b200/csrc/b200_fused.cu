@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::N
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
               double *__restrict__ gradu, const double *__restrict__ x, double *__restrict__ y,
-              const unsigned *__restrict__ scat_tab, int offsets_ahead, double *__restrict__ evec) {
+              const unsigned *__restrict__ scat_tab, int offsets_ahead, double *__restrict__ evec, int x_ahead, int slab_ahead) {
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, Q3 = Cfg<Q>::Q3, P3 = P * P * P;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = apply_sc(P, Q), SE = apply_se(Q, SC);
   constexpr int NC = MODE == MODE_JACOBIAN ? JCache<PROB>::N : 10;
@@ -123,7 +123,14 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   // per-point data of this CTA: slab base + lane offset, plane stride (q-blocked layout)
   const size_t ebt = FULL ? (size_t)(EB * T) : (size_t)ebn * T;
   const double *qlane = qa + (size_t)blk * EB * NC * Q3 + (FULL ? tid : t * ebn + eb);
-  if (tid == 0) l2_prefetch_bulk(qa + (size_t)blk * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
+  // slab_ahead = 0: the CTA asks for its OWN slab at its start (it needs it ~4 us later, in the point-function stage);
+  // > 0 (full groups only): for the slab of the CTA that many groups later, so that a slab is in L2 before its CTA starts
+  if (tid == 0) {
+    if (!FULL || slab_ahead <= 0 || blk < slab_ahead)
+      l2_prefetch_bulk(qa + (size_t)blk * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
+    if (FULL && slab_ahead > 0 && (long long)(blk + slab_ahead + 1) * EB <= nelem)
+      l2_prefetch_bulk(qa + (size_t)(blk + slab_ahead) * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
+  }
   // ... and the element offsets of a CTA that starts about one wave of resident CTAs later: its gather then
   // begins with an L2 hit instead of a DRAM round trip in front of the dependent loads of x
   if (FULL && tid == 32 && offsets_ahead > 0 && (long long)(blk + offsets_ahead + 1) * EB <= nelem)
@@ -137,6 +144,17 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
     int o[P];
 #pragma unroll
     for (int k = 0; k < P; k++) o[k] = __ldg(off + k * P * P);
+    // the L-vector entries a CTA x_ahead groups later will gather: its offsets are in L2 already (prefetched by an
+    // earlier CTA), so this costs one L2 round trip that nothing waits for; the later CTA's dependent second load
+    // then finds x in L2 instead of DRAM
+    if (FULL && x_ahead > 0 && (long long)(blk + x_ahead + 1) * EB <= nelem) {
+      const int *offn = off + (size_t)x_ahead * EB * P3;
+      int on[P];
+#pragma unroll
+      for (int k = 0; k < P; k++) on[k] = __ldg(offn + k * P * P);
+#pragma unroll
+      for (int k = 0; k < P; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + on[k]));
+    }
 #pragma unroll
     for (int k = 0; k < P; k++) {
       soff[eb * P3 + (k * P + b) * P + a] = o[k];  // parked for the scatter at the end
@@ -769,6 +787,10 @@ template <int P, int Q> static int cached_mats(const double *hB, const double *h
 
 // one wave of resident CTAs (5 per SM on 148 SMs), rounded up: how far ahead a CTA prefetches element offsets
 constexpr int OFFSETS_AHEAD = 1024;
+// how many groups ahead a CTA prefetches the L-vector entries of a later gather (0 = off; must stay below OFFSETS_AHEAD)
+constexpr int X_AHEAD = 0;
+// how many groups ahead a CTA requests the per-point slab (0 = its own)
+constexpr int SLAB_AHEAD = 0;
 
 template <int P, int Q, int PROB, int MODE>
 static int launch_apply(const Material &mt, int nelem, const double *hB, const double *hD, const int *offsets,
@@ -801,22 +823,24 @@ static int launch_apply(const Material &mt, int nelem, const double *hB, const d
   const unsigned *d_tab = static_cast<const unsigned *>(pd.table[dev]);
 #ifdef B200_NO_FULL
   if (nelem) {
-    kern_tail<<<(nelem + EB - 1) / EB, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y, d_tab, 0, evec);
+    kern_tail<<<(nelem + EB - 1) / EB, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nelem, offsets, qa, gradu, x, y, d_tab, 0, evec, 0, 0);
     B200_LAUNCH_CHECK("k_fused_apply");
     return 0;
   }
 #endif
   static const int ahead = getenv("B200_OFFSETS_AHEAD") ? atoi(getenv("B200_OFFSETS_AHEAD")) : OFFSETS_AHEAD;
+  static const int xahead = getenv("B200_X_AHEAD") ? atoi(getenv("B200_X_AHEAD")) : X_AHEAD;
+  static const int sahead = getenv("B200_SLAB_AHEAD") ? atoi(getenv("B200_SLAB_AHEAD")) : SLAB_AHEAD;
   const int nfull = nelem / EB, ntail = nelem - nfull * EB;
   if (nfull) {
-    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, ahead, evec);
+    kern<<<nfull, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, nfull * EB, offsets, qa, gradu, x, y, d_tab, ahead, evec, xahead, sahead);
     B200_LAUNCH_CHECK("k_fused_apply");
   }
   if (ntail) {  // the partial group at the end of the element range: same kernel with run-time group extent
     const size_t e0 = (size_t)nfull * EB;
     kern_tail<<<1, Cfg<Q>::NT, smem_bytes, g_stream>>>(m, mt, ntail, offsets + e0 * P3, qa + e0 * NC * Q3,
                                                        gradu ? gradu + e0 * 9 * Q3 : nullptr, x, y, d_tab, 0,
-                                                       evec ? evec + e0 * 3 * P3 : nullptr);
+                                                       evec ? evec + e0 * 3 * P3 : nullptr, 0, 0);
     B200_LAUNCH_CHECK("k_fused_apply(tail)");
   }
   return 0;

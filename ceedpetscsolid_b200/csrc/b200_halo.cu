@@ -196,11 +196,18 @@ int b200_halo_destroy(b200_halo *h) {
   return 0;
 }
 
-// every partial sum on a shared dof must be complete on the compute stream when this is called
-int b200_halo_begin(b200_halo *h, const double *d_y) {
-  if (h->sg.n == 0) return 0;
+// Fork: the side stream waits for everything queued on the compute stream so far and is returned, so that the caller
+// can queue the work that PRODUCES the interface partial sums on it (b200_set_stream(side) ... b200_set_stream(main))
+// while the compute stream carries on with work that does not touch shared dofs.  b200_halo_begin_forked then pushes
+// behind that work without another event.
+int b200_halo_fork(b200_halo *h, void **side_stream) {
   B200_CHECK(cudaEventRecord(h->ev_ready, g_stream));
   B200_CHECK(cudaStreamWaitEvent(h->side, h->ev_ready, 0));
+  *side_stream = (void *)h->side;
+  return 0;
+}
+
+static int halo_push_on_side(b200_halo *h, const double *d_y) {
   if (h->total) {
     size_t nb = (h->total + 255) / 256;
     if (nb > 148 * 4) nb = 148 * 4;
@@ -213,8 +220,28 @@ int b200_halo_begin(b200_halo *h, const double *d_y) {
   return 0;
 }
 
-int b200_halo_end(b200_halo *h, double *d_y) {
+// after b200_halo_fork: the interface partial sums are produced by work already queued on the side stream
+int b200_halo_begin_forked(b200_halo *h, const double *d_y) {
+  if (h->sg.n == 0) {   // nothing to exchange, but the compute stream must still join the side stream's work
+    B200_CHECK(cudaEventRecord(h->ev_pushed, h->side));
+    return 0;
+  }
+  return halo_push_on_side(h, d_y);
+}
+
+// every partial sum on a shared dof must be complete on the compute stream when this is called
+int b200_halo_begin(b200_halo *h, const double *d_y) {
   if (h->sg.n == 0) return 0;
+  B200_CHECK(cudaEventRecord(h->ev_ready, g_stream));
+  B200_CHECK(cudaStreamWaitEvent(h->side, h->ev_ready, 0));
+  return halo_push_on_side(h, d_y);
+}
+
+int b200_halo_end(b200_halo *h, double *d_y) {
+  if (h->sg.n == 0) {   // joins a forked side stream (no-op otherwise: the event is then already complete)
+    B200_CHECK(cudaStreamWaitEvent(g_stream, h->ev_pushed, 0));
+    return 0;
+  }
   // my own partial sums must have left (push reads y) before the unpack overwrites them with the totals
   B200_CHECK(cudaStreamWaitEvent(g_stream, h->ev_pushed, 0));
   size_t nb = ((size_t)h->nuniq + 255) / 256;

@@ -1438,9 +1438,20 @@ int CeedOperatorApplyPartitionedB200(CeedOperator op, CeedVector in, CeedVector 
     CeedChk(vec_dev_rw(out, &y));
     if (halo) { B2(ceed, b200_halo_begin((b200_halo *)halo, y)); B2(ceed, b200_halo_end((b200_halo *)halo, y)); }
   } else {
-    CeedChk(op_apply_fused_range(op, in, out, 0, n_interface));
+    /* everything the two element ranges share is made current on the compute stream first (device copies of the
+       vectors, the Jacobian cache); then the interface elements + push run on the halo's high-priority side stream
+       CONCURRENTLY with the interior elements on the compute stream (both only add into Y, on disjoint shared dofs) */
+    const double *x, *jc;
+    CeedChk(vec_dev_read(in, &x));
     CeedChk(vec_dev_rw(out, &y));
-    B2(ceed, b200_halo_begin((b200_halo *)halo, y));
+    if (op->kind == OP_FUSED_JACOBIAN) CeedChk(jcache_get(op, &jc));
+    void *side = NULL, *mainstream = b200_get_stream();
+    B2(ceed, b200_halo_fork((b200_halo *)halo, &side));
+    B2(ceed, b200_set_stream(side));
+    int rc = op_apply_fused_range(op, in, out, 0, n_interface);
+    b200_set_stream(mainstream);
+    if (rc) return rc;
+    B2(ceed, b200_halo_begin_forked((b200_halo *)halo, y));
     CeedChk(op_apply_fused_range(op, in, out, n_interface, nelem));
     B2(ceed, b200_halo_end((b200_halo *)halo, y));
   }

@@ -242,6 +242,11 @@ int b200_halo_create(int nnbr, const int *seg_start, double *const *remote_p0, d
                      const int *d_udof, const int *d_uptr, const int *d_uent, double timeout_s, b200_halo **out);
 int b200_halo_destroy(b200_halo *h);
 int b200_halo_begin(b200_halo *h, const double *d_y);
+/* fork/begin_forked: the work that produces the interface partial sums is queued on the halo's side stream
+ * (b200_halo_fork orders it behind the compute stream and returns it; the caller switches b200_set_stream to it and
+ * back), so it runs CONCURRENTLY with shared-dof-free work on the compute stream; the push follows it on the side stream */
+int b200_halo_fork(b200_halo *h, void **side_stream);
+int b200_halo_begin_forked(b200_halo *h, const double *d_y);
 int b200_halo_end(b200_halo *h, double *d_y);
 int b200_halo_error(b200_halo *h, int *err);   /* synchronises; *err != 0: an exchange timed out */
 /* the same ordered sum for exchanges carried by a communication library (d_recv laid out like a window) */

@@ -44,4 +44,5 @@ xc.set_array(x); yc.set_array(y)
 jac = min(timeit(lambda: data[fine].opJacob.apply_add(xc, yc)) for _ in range(3))
 diag = timeit(lambda: data[fine].opJacob.linear_assemble_diagonal(yc), reps=5, warm=1)
 print(f"{os.environ.get('CEED_B200_LIB', 'default').split('libceed_b200')[-1]:24s} ahead={os.environ.get('B200_OFFSETS_AHEAD', 'dflt'):6s} "
+      f"x_ahead={os.environ.get('B200_X_AHEAD', 'dflt'):5s} slab_ahead={os.environ.get('B200_SLAB_AHEAD', 'dflt'):5s} "
       f"jacobian {jac:.4f} ms  residual {res:.4f} ms  diagonal {diag:.4f} ms")
