@@ -220,3 +220,38 @@ def test_host_resident_vectors_take_the_pipelined_path(G, problem, p, n, perm):
             assert rel_err(yh.numpy(), ref) < 1e-13
             # x is current on the device afterwards: a second, device-side use must not need the host copy
             xc.destroy(); yc.destroy()
+
+
+def test_partitioned_apply_without_a_halo_equals_apply_plus_mask():
+    """CeedOperatorApplyPartitionedB200 on one rank (halo = NULL): zero, fused operator, Dirichlet rows zeroed --
+    bit-for-bit what CeedOperatorApply followed by the mask gives when the scatter is deterministic, and to round-off
+    with atomics; element counts that are not a multiple of the group size are refused for the interface split."""
+    import torch
+    import gpu_helpers as G
+    from ceedpetscsolid_b200 import ceed as libceed
+    for resource in ("/gpu/b200", "/gpu/b200:deterministic"):
+        g = G.GpuProblem("hyperFS", (3, 2, 2), 4, resource=resource)
+        g.residual()
+        fine = len(g.degrees) - 1
+        op = g.data[fine].opJacob
+        n = g.mesh.lsize(4)
+        x = torch.randn(n, dtype=torch.float64, device="cuda")
+        y1, y2 = torch.full_like(x, 7.0), torch.full_like(x, -3.0)
+        mask = torch.arange(0, n, 5, dtype=torch.int32, device="cuda")
+        xc, yc = g.ceed.Vector(n), g.ceed.Vector(n)
+        xc.set_array(x); yc.set_array(y1)
+        op.apply(xc, yc)
+        yc.take_array()
+        y1[mask.long()] = 0.0
+        yc.set_array(y2)
+        op.apply_partitioned(xc, yc, 0, None, mask)
+        yc.take_array()
+        torch.cuda.synchronize()
+        if "deterministic" in resource:
+            assert torch.equal(y1, y2)
+        else:
+            assert float((y1 - y2).norm() / y1.norm()) < 1e-14
+        yc.set_array(y2)
+        with pytest.raises(libceed.CeedError, match="n_interface"):
+            op.apply_partitioned(xc, yc, 3, None, mask)          # not a multiple of the element-group size
+        yc.take_array(); xc.take_array()
