@@ -503,6 +503,8 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
   double *R = smem + eb * SE;  // 9 single-component lattices: terms 0..5, then the three z-selector sums
   const double *qlane = jcp + (size_t)blk * EB * NC * Q3 + (size_t)(t * ebn + eb);
   const size_t ebt = (size_t)ebn * T;
+  // the CTA's whole slab in one bulk L2 request: the first sweep then reads from L2 like the other two
+  if (tid == 0) l2_prefetch_bulk(jcp + (size_t)blk * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
 
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
