@@ -17,11 +17,15 @@
 //   x-lines: d/dx in registers;  y-lines, z-lines: d/dy, d/dz with the collocated
 //   derivative matrix Gc (Gc B = D);  x-lines again: QFunction at the thread's Q points,
 //   streaming the q-blocked per-point data straight from HBM (fully coalesced);
-//   then the exact transpose back to z-lines and an atomic scatter-add.
+//   then the exact transpose back, the nodal output written interlaced [node][component],
+//   and a scatter sweep in L-vector order (FP64 atomics, or plain stores to an E-vector
+//   in deterministic mode).
 //
-// FP64 work at P=Q=5: 12 line stages x 1875 DFMA + 125 x ~105 (hyperFS Jacobian from the
-// Jacobian cache) ~ 36 k per element, vs ~100 k for libCEED-style 9-contraction gradients
-// around the unmodified QFunction.  See DESIGN.md for the roofline arithmetic.
+// FP64 work at P=Q=5: 12 line stages x 1875 DFMA + 125 x ~150 (hyperFS Jacobian from the
+// Jacobian cache) ~ 41 k per element, vs ~100 k for libCEED-style 9-contraction gradients
+// around the unmodified QFunction.  The binding unit is the L1TEX data pipe (25 lattice passes
+// through shared memory + the stream + gather/scatter: 86 % busy); see DESIGN.md section 3 and
+// profiles/r2_k_fused_apply_full.md.
 #include "b200_qf.cuh"
 
 #include <stdlib.h>
