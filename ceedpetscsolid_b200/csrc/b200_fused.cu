@@ -510,6 +510,10 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
   // the CTA's whole slab in one bulk L2 request: the first sweep then reads from L2 like the other two
   if (tid == 0) l2_prefetch_bulk(jcp + (size_t)blk * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
 
+  // (M, kappa) of the thread's Q points, computed in the first sweep and kept in shared memory for the other two
+  // components: private to the thread (same x-line owner in every sweep), [7][Q][lane] -> no barrier, no conflicts
+  double *MK = smem + EB * SE + tid;
+  constexpr int MKS = T * EB;  // lane stride
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
     if (act) {
@@ -518,29 +522,49 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
       for (int tt = 0; tt < 6; tt++)
 #pragma unroll
         for (int i = 0; i < P; i++) S[tt][i] = 0;
-      double qn[NC];
+      if (c == 0) {
+        double qn[NC];
 #pragma unroll
-      for (int n = 0; n < NC; n++) qn[n] = __ldg(qlane + (size_t)(n * Q) * ebt);
+        for (int n = 0; n < NC; n++) qn[n] = __ldg(qlane + (size_t)(n * Q) * ebt);
 #pragma unroll 1
-      for (int qx = 0; qx < Q; qx++) {
-        double qd[NC], M[6], kappa;
+        for (int qx = 0; qx < Q; qx++) {
+          double qd[NC], M[6], kappa;
 #pragma unroll
-        for (int n = 0; n < NC; n++) qd[n] = qn[n];
-        if (qx + 1 < Q) {
+          for (int n = 0; n < NC; n++) qd[n] = qn[n];
+          if (qx + 1 < Q) {
 #pragma unroll
-          for (int n = 0; n < NC; n++) qn[n] = __ldg(qlane + (size_t)(n * Q + qx + 1) * ebt);
+            for (int n = 0; n < NC; n++) qn[n] = __ldg(qlane + (size_t)(n * Q + qx + 1) * ebt);
+          }
+          diag_blocks_point<PROB>(mt, qd, M, kappa);
+#pragma unroll
+          for (int tt = 0; tt < 6; tt++) MK[(tt * Q + qx) * MKS] = M[tt];
+          MK[(6 * Q + qx) * MKS] = kappa;
+          const double kc[3] = {qd[0], qd[3], qd[6]};
+#pragma unroll
+          for (int tt = 0; tt < 6; tt++) {
+            double At = M[tt] + kappa * kc[VJ[tt]] * kc[VK[tt]];
+            if (tt >= 3) At += At;
+#pragma unroll
+            for (int i = 0; i < P; i++) S[tt][i] += dm.M[SELX[tt]][qx * P + i] * At;
+          }
         }
-        diag_blocks_point<PROB>(mt, qd, M, kappa);
-        const double k0 = c == 0 ? qd[0] : (c == 1 ? qd[1] : qd[2]);
-        const double k1 = c == 0 ? qd[3] : (c == 1 ? qd[4] : qd[5]);
-        const double k2 = c == 0 ? qd[6] : (c == 1 ? qd[7] : qd[8]);
-        const double kc[3] = {k0, k1, k2};
+      } else {
+        // K column c of every point of the line (L2 hits: the slab was read in the first sweep)
+        double kq[Q][3];
 #pragma unroll
-        for (int tt = 0; tt < 6; tt++) {
-          double At = M[tt] + kappa * kc[VJ[tt]] * kc[VK[tt]];
-          if (tt >= 3) At += At;
+        for (int qx = 0; qx < Q; qx++)
 #pragma unroll
-          for (int i = 0; i < P; i++) S[tt][i] += dm.M[SELX[tt]][qx * P + i] * At;
+          for (int d = 0; d < 3; d++) kq[qx][d] = __ldg(qlane + (size_t)((3 * d + c) * Q + qx) * ebt);
+#pragma unroll
+        for (int qx = 0; qx < Q; qx++) {
+          const double kappa = MK[(6 * Q + qx) * MKS];
+#pragma unroll
+          for (int tt = 0; tt < 6; tt++) {
+            double At = MK[(tt * Q + qx) * MKS] + kappa * kq[qx][VJ[tt]] * kq[qx][VK[tt]];
+            if (tt >= 3) At += At;
+#pragma unroll
+            for (int i = 0; i < P; i++) S[tt][i] += dm.M[SELX[tt]][qx * P + i] * At;
+          }
         }
       }
 #pragma unroll
@@ -862,16 +886,18 @@ static int launch_diag(const Material &mt, int nelem, const double *hB, const do
     dm.M[2][i] = hD[i] * hD[i];
   }
   auto kern = k_fused_diag<P, Q, PROB>;
+  // nine lattices per element + the per-thread (M, kappa) store of the first sweep
+  constexpr size_t diag_smem = Cfg<Q>::SMEM + sizeof(double) * 7 * Q * Cfg<Q>::T * Cfg<Q>::EB;
   static PerDevice pd;
   int dev;
   if (int rc = current_device(&dev)) return rc;
   if (!pd.configured[dev]) {
-    if (int rc = opt_in_smem(kern, Cfg<Q>::SMEM)) return rc;
+    if (int rc = opt_in_smem(kern, diag_smem)) return rc;
     pd.configured[dev] = true;
   }
   const int nblk = (nelem + Cfg<Q>::EB - 1) / Cfg<Q>::EB;
   if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<Q>::NT, Cfg<Q>::SMEM, g_stream>>>(dm, mt, nelem, offsets, jc, diag, evec);
+  kern<<<nblk, Cfg<Q>::NT, diag_smem, g_stream>>>(dm, mt, nelem, offsets, jc, diag, evec);
   B200_LAUNCH_CHECK("k_fused_diag");
   return 0;
 }
