@@ -15,8 +15,8 @@ def G():
     return gpu_helpers
 
 
-CASES = [  # problem, n, p, qextra, perm
-    ("linElas", 3, 1, 0, None), ("linElas", 4, 2, 0, None), ("linElas", 3, 3, 0, 11),
+CASES = [  # problem, n, p, qextra, perm      (("linElas", 8, 2): BASELINE configs[0] = C1 exactly)
+    ("linElas", 3, 1, 0, None), ("linElas", 4, 2, 0, None), ("linElas", 8, 2, 0, None), ("linElas", 3, 3, 0, 11),
     ("hyperSS", 3, 2, 0, None), ("hyperSS", 4, 3, 0, None), ("hyperSS", 2, 4, 0, 12),
     ("hyperFS", 3, 2, 0, None), ("hyperFS", 3, 3, 0, None), ("hyperFS", 3, 4, 0, None),
     ("hyperFS", 2, 4, 1, None), ("hyperFS", 2, 2, 1, 13), ("hyperFS", (7, 2, 3), 4, 0, None),
