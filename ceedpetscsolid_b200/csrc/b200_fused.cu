@@ -107,6 +107,12 @@ template <int P, int Q, int PROB, int MODE, bool FULL>
 #ifndef B200_RES_AHEAD
 #define B200_RES_AHEAD 1
 #endif
+#ifndef B200_RES_ROLLED
+#define B200_RES_ROLLED 0
+#endif
+#ifndef B200_JAC_ROLLED
+#define B200_JAC_ROLLED 0
+#endif
 __global__ void __launch_bounds__(Cfg<Q>::NT, MODE == MODE_JACOBIAN ? (Cfg<Q>::NT <= 128 ? B200_JAC_CTAS : 2) : (Cfg<Q>::NT <= 128 ? B200_RES_CTAS : 1))
 k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Material mt, int nelem,
               const int *__restrict__ offsets, const double *__restrict__ qa,
@@ -255,7 +261,81 @@ k_fused_apply(const __grid_constant__ Mats<P, Q> m, const __grid_constant__ Mate
   }
   __syncthreads();
   // ---- phase 5: QFunction at the Q points of this x-line; phase 6: d/dx^T in registers
-  if (act) {
+  // ROLLED (tuning switch, OFF): the loop over the Q points of the line not unrolled.  Fully unrolled, the hyperFS
+  // residual kernel is 3 120 instructions (50 kB), past the instruction-cache plateau, and ncu attributes 24 % of its
+  // stall samples to instruction fetch (no_inst); rolled (the line values rotate through a register array with static
+  // indices: Hx[.][0] is consumed, the array shifts left, the new W[.][0] enters at the end) it is 2 168 instructions --
+  // but MEASURED SLOWER: residual 1.59 vs 1.45 ms, Jacobian 1.82 vs 1.13 ms at 64^3 (the scheduler loses the overlap of
+  // one point's loads and stores with the next point's arithmetic).  Kept for the record.
+  constexpr bool ROLLED = MODE == MODE_RESIDUAL ? (B200_RES_ROLLED != 0) : (B200_JAC_ROLLED != 0);
+  if (act && ROLLED) {
+    const double *qp = qlane;                                    // advances by one plane per point
+    double *g1 = R1 + IDX(0, 0, a, b), *g2 = R2 + IDX(0, 0, a, b);
+    double *gslab = (MODE == MODE_RESIDUAL && PROB != B200_PROB_LINELAS)
+                        ? gradu + (size_t)blk * EB * 9 * Q3 + (FULL ? tid : t * ebn + eb) : nullptr;
+#pragma unroll 1
+    for (int qx = 0; qx < Q; qx++) {
+      double qd[NC], H[3][3], W[3][3];
+      if (AHEAD) {
+#pragma unroll
+        for (int n = 0; n < NC; n++) qd[n] = qn[n];
+        if (qx + 1 < Q) {
+#pragma unroll
+          for (int n = 0; n < NC; n++) qn[n] = ld_stream(qp + (size_t)(n * Q + 1) * ebt);
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NC; n++) qd[n] = ld_stream(qp + (size_t)(n * Q) * ebt);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        H[c][0] = Hx[c][0];
+        H[c][1] = g1[c * SC];
+        H[c][2] = g2[c * SC];
+      }
+      if (MODE == MODE_JACOBIAN) {
+        jacobian_point<PROB>(mt, qd, H, W);
+      } else {
+        double A[3][3], g[3][3];
+#pragma unroll
+        for (int mm = 0; mm < 3; mm++)
+#pragma unroll
+          for (int k = 0; k < 3; k++) A[mm][k] = qd[1 + 3 * mm + k];
+        if (PROB == B200_PROB_LINELAS) {
+          linelas_point(mt, qd[0], A, H, W);
+        } else {
+          if (PROB == B200_PROB_HYPERSS) hyperss_f_point(mt, qd[0], A, H, g, W);
+          else hyperfs_f_point(mt, qd[0], A, H, g, W);
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) __stcs(gslab + (size_t)((c * 3 + k) * Q) * ebt, g[c][k]);
+          gslab += ebt;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int i = 0; i + 1 < Q; i++) Hx[c][i] = Hx[c][i + 1];
+        Hx[c][Q - 1] = W[c][0];
+        g1[c * SC] = W[c][1];
+        g2[c * SC] = W[c][2];
+      }
+      qp += ebt;
+      g1++;
+      g2++;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int qx = 0; qx < Q; qx++) {
+        double s = 0;
+#pragma unroll
+        for (int mm = 0; mm < Q; mm++) s += m.Gc[mm * Q + qx] * Hx[c][mm];
+        R0[IDX(c, qx, a, b)] = s;
+      }
+  }
+  if (act && !ROLLED) {
     double Wx[3][Q];
 #pragma unroll
     for (int qx = 0; qx < Q; qx++) {
@@ -482,7 +562,7 @@ template <int P, int Q> struct DiagMats {
   double M[3][Q * P];  // [0] B.B  [1] B.D  [2] D.D   (element-wise, [Q][P])
 };
 
-template <int P, int Q, int PROB>
+template <int P, int Q, int PROB, bool FULL>
 #ifndef B200_DIAG_THREADS
 #define B200_DIAG_THREADS 384
 #endif
@@ -501,12 +581,12 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
   const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
   const int blk = blockIdx.x;
   const int rem = nelem - blk * EB;
-  const int ebn = rem < EB ? rem : EB;
-  const bool act = t < T && eb < ebn;
+  const int ebn = FULL ? EB : (rem < EB ? rem : EB);   // FULL: compile-time plane strides (tail group: second launch)
+  const bool act = t < T && (FULL || eb < ebn);
   const int e = blk * EB + eb;
   double *R = smem + eb * SE;  // 9 single-component lattices: terms 0..5, then the three z-selector sums
-  const double *qlane = jcp + (size_t)blk * EB * NC * Q3 + (size_t)(t * ebn + eb);
-  const size_t ebt = (size_t)ebn * T;
+  const double *qlane = jcp + (size_t)blk * EB * NC * Q3 + (size_t)(FULL ? tid : t * ebn + eb);
+  const size_t ebt = FULL ? (size_t)(EB * T) : (size_t)ebn * T;
   // the CTA's whole slab in one bulk L2 request: the first sweep then reads from L2 like the other two
   if (tid == 0) l2_prefetch_bulk(jcp + (size_t)blk * EB * NC * Q3, (unsigned)(ebt * Q * NC * sizeof(double)));
 
@@ -885,20 +965,30 @@ static int launch_diag(const Material &mt, int nelem, const double *hB, const do
     dm.M[1][i] = hB[i] * hD[i];
     dm.M[2][i] = hD[i] * hD[i];
   }
-  auto kern = k_fused_diag<P, Q, PROB>;
+  auto kern = k_fused_diag<P, Q, PROB, true>;
+  auto kern_tail = k_fused_diag<P, Q, PROB, false>;
   // nine lattices per element + the per-thread (M, kappa) store of the first sweep
   constexpr size_t diag_smem = Cfg<Q>::SMEM + sizeof(double) * 7 * Q * Cfg<Q>::T * Cfg<Q>::EB;
+  constexpr int EB = Cfg<Q>::EB, P3 = P * P * P, Q3 = Q * Q * Q, NC = JCache<PROB>::N;
   static PerDevice pd;
   int dev;
   if (int rc = current_device(&dev)) return rc;
   if (!pd.configured[dev]) {
     if (int rc = opt_in_smem(kern, diag_smem)) return rc;
+    if (int rc = opt_in_smem(kern_tail, diag_smem)) return rc;
     pd.configured[dev] = true;
   }
-  const int nblk = (nelem + Cfg<Q>::EB - 1) / Cfg<Q>::EB;
-  if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<Q>::NT, diag_smem, g_stream>>>(dm, mt, nelem, offsets, jc, diag, evec);
-  B200_LAUNCH_CHECK("k_fused_diag");
+  const int nfull = nelem / EB, ntail = nelem - nfull * EB;
+  if (nfull) {
+    kern<<<nfull, Cfg<Q>::NT, diag_smem, g_stream>>>(dm, mt, nfull * EB, offsets, jc, diag, evec);
+    B200_LAUNCH_CHECK("k_fused_diag");
+  }
+  if (ntail) {
+    const size_t e0 = (size_t)nfull * EB;
+    kern_tail<<<1, Cfg<Q>::NT, diag_smem, g_stream>>>(dm, mt, ntail, offsets + e0 * P3, jc + e0 * NC * Q3, diag,
+                                                      evec ? evec + e0 * 3 * P3 : nullptr);
+    B200_LAUNCH_CHECK("k_fused_diag(tail)");
+  }
   return 0;
 }
 
