@@ -74,7 +74,18 @@ PetscErrorCode VecCUDAGetArrayRead(Vec v, const PetscScalar **a) { return get_de
 PetscErrorCode VecCUDARestoreArray(Vec v, PetscScalar **a) { (void)v; if (a) *a = NULL; return 0; }
 PetscErrorCode VecCUDARestoreArrayRead(Vec v, const PetscScalar **a) { (void)v; if (a) *a = NULL; return 0; }
 PetscErrorCode VecGetDM(Vec v, DM *dm) { *dm = v->dm; return 0; }
-PetscErrorCode VecView(Vec v, PetscViewer viewer) { (void)v; (void)viewer; return 0; }
+/* the "VTK viewer": keeps a host copy of the last vector viewed, for the test driver to write out */
+double *petsc_mini_viewed = NULL;
+PetscInt petsc_mini_viewed_n = 0;
+PetscErrorCode VecView(Vec v, PetscViewer viewer) {
+  (void)viewer;
+  free(petsc_mini_viewed);
+  petsc_mini_viewed = (double *)malloc(sizeof(double) * (size_t)(v->n ? v->n : 1));
+  petsc_mini_viewed_n = v->n;
+  if (v->device) B2CHK(b200_memcpy_d2h(petsc_mini_viewed, v->a, sizeof(double) * (size_t)v->n));
+  else memcpy(petsc_mini_viewed, v->a, sizeof(double) * (size_t)v->n);
+  return 0;
+}
 
 /* ---------------------------------------------------------------- DM */
 PetscErrorCode DMGetDimension(DM dm, PetscInt *dim) { *dim = dm->dim; return 0; }

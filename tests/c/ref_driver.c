@@ -9,6 +9,7 @@
  *   SetupJacobianCtx, SetupProlongRestrictCtx                         misc.c:26-146
  *   FormResidual_Ceed, ApplyJacobian_Ceed, GetDiag_Ceed,
  *   Prolong_Ceed, Restrict_Ceed, ComputeStrainEnergy                  matops.c:63-300
+ *   ViewDiagnosticQuantities (its VecView captured instead of written) misc.c:217-300
  *
  * so the libCEED objects are created, wired and applied by the reference's code, the QFunction pointers are the
  * reference's own (which also exercises the backend's QFunction guard), and only the mesh (box, lexicographic
@@ -21,6 +22,8 @@
 
 #include "b200_kernels.h"
 
+extern double *petsc_mini_viewed;   /* last vector passed to VecView (petsc_mini.c) */
+extern PetscInt petsc_mini_viewed_n;
 static FILE *fin;
 static int rd_i(void) { int v; if (fread(&v, sizeof v, 1, fin) != 1) { fprintf(stderr, "ref_driver: short input\n"); exit(2); } return v; }
 static int *rd_iv(size_t n) {
@@ -40,6 +43,14 @@ static int *to_device_i(const int *h, size_t n) {
     exit(3);
   }
   return d;
+}
+
+/* a DM without constraints: global = local */
+static void identity_maps(DM dm) {
+  dm->l2g = (int *)malloc(sizeof(int) * (size_t)dm->lsize);
+  for (int i = 0; i < dm->lsize; i++) dm->l2g[i] = i;
+  dm->g2l = dm->l2g;
+  if (dm->device) dm->d_l2g_loc = to_device_i(dm->g2l, (size_t)dm->gsize);
 }
 
 /* solution-space DM of one level from the input stream */
@@ -195,6 +206,17 @@ int main(int argc, char **argv) {
   PetscReal energy = 0;
   CHK(ComputeStrainEnergy(dmEnergy, resCtx, ceedData[fineLevel]->opEnergy, U, &energy));
   fwrite(&energy, sizeof energy, 1, fout);
+  { /* nodal diagnostic quantities, as elasticity.c:835-850 sets them up */
+    identity_maps(dmDiagnostic);
+    UserMult diagnosticCtx = (UserMult)calloc(1, sizeof *diagnosticCtx);
+    memcpy(diagnosticCtx, resCtx, sizeof *resCtx);
+    diagnosticCtx->dm = dmDiagnostic;
+    diagnosticCtx->op = ceedData[fineLevel]->opDiagnostic;
+    CHK(ViewDiagnosticQuantities(0, fine, diagnosticCtx, U, ceedData[fineLevel]->ErestrictDiagnostic));
+    if (petsc_mini_viewed_n != dmDiagnostic->gsize) { fprintf(stderr, "ref_driver: diagnostic vector was not viewed\n"); return 5; }
+    fwrite(petsc_mini_viewed, sizeof(double), (size_t)petsc_mini_viewed_n, fout);
+    free(diagnosticCtx);
+  }
   fclose(fout);
   fclose(fin);
   int det = 0;

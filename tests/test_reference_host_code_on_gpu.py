@@ -6,7 +6,7 @@ copied -- against this repository's <ceed.h> / libceed_b200.so and a functional 
 (tests/c/petsc_mini).  The reference's SetupLibceedFineLevel / SetupLibceedLevel build every libCEED object (with the
 reference's own QFunction pointers: the backend's QFunction guard runs on them), SetupJacobianCtx /
 SetupProlongRestrictCtx wire the MatShell contexts, and FormResidual_Ceed, ApplyJacobian_Ceed, GetDiag_Ceed,
-Prolong_Ceed, Restrict_Ceed and ComputeStrainEnergy are the reference's functions.  This test writes the mesh
+Prolong_Ceed, Restrict_Ceed, ComputeStrainEnergy and ViewDiagnosticQuantities are the reference's functions.  This test writes the mesh
 (closure indices with essential-BC dofs encoded as -(loc+1), as DMPlex hands them to CreateRestrictionPlex) and
 the vectors, runs the driver with host and with device memtype, and compares every output with the CPU oracle.
 """
@@ -120,9 +120,14 @@ def test_reference_setup_and_matshell_callbacks_drive_the_backend(tmp_path, prob
         assert rel_err(take(xs[l].size), yp[frees[l]]) < TOL, ("prolong", pf)
         yr = oracle.transfer(True, o.nelem, pc + 1, pf + 1, offc, offf, locals_x[l] * minv, lc)
         assert rel_err(take(xs[l - 1].size), yr[frees[l - 1]]) < TOL, ("restrict", pf)
-    e_ref, _ = _oracle_post(problem, mesh, p, o.u_fine)
+    e_ref, d_ref = _oracle_post(problem, mesh, p, o.u_fine)
     energy = take(1)[0]
     assert abs(energy - e_ref) < TOL * abs(e_ref)
+    # ViewDiagnosticQuantities (misc.c:217-300): (u, pressure, two strain invariants, volume ratio, energy density) per node
+    diag = take(8 * mesh.num_nodes(p)).reshape(-1, 8)
+    assert rel_err(diag[:, :3], o.u_fine.reshape(-1, 3)) < TOL
+    for k in range(3, 8):
+        assert rel_err(diag[:, k], d_ref[:, k]) < TOL, ("diagnostic", k)
     assert pos == res.size
 
 
