@@ -329,6 +329,17 @@ static int vec_dev_rw(CeedVector v, double **p) {
   return 0;
 }
 
+/* A host array borrowed with CEED_USE_POINTER is written in place by /cpu/self, and the reference relies on that:
+ * ViewDiagnosticQuantities reads the borrowed array between CeedOperatorApply and CeedVectorTakeArray
+ * (misc.c:258-268).  The public entry points that produce an output therefore bring a borrowed host array up to
+ * date before they return; CeedVectorTakeArray then finds it current, so the MatMult path (matops.c:44-50) still
+ * pays one device-to-host copy per product, not two. */
+static int vec_write_through(CeedVector v) {
+  if (!v || v == CEED_VECTOR_NONE || v == CEED_VECTOR_ACTIVE) return 0;
+  if (v->h && !v->h_owned && !v->h_valid && v->d_valid) CeedChk(vec_sync(v, CEED_MEM_HOST));
+  return 0;
+}
+
 int CeedVectorSetArray(CeedVector vec, CeedMemType mtype, CeedCopyMode cmode, CeedScalar *array) {
   Ceed ceed = vec->ceed;
   if (!array) return CeedError(ceed, 1, "CeedVectorSetArray: NULL array");
@@ -566,7 +577,7 @@ int CeedElemRestrictionGetMultiplicity(CeedElemRestriction rstr, CeedVector mult
   CeedChk(rstr_apply_raw(rstr, 1, ones, m));
   B2(ceed, b200_sync());
   B2(ceed, b200_free(ones));
-  return 0;
+  return vec_write_through(mult);
 }
 int CeedElemRestrictionGetNumElements(CeedElemRestriction r, CeedInt *n) { *n = r->nelem; return 0; }
 int CeedElemRestrictionGetElementSize(CeedElemRestriction r, CeedInt *n) { *n = r->elemsize; return 0; }
@@ -1342,11 +1353,10 @@ static int op_apply_fused_range(CeedOperator op, CeedVector in, CeedVector out, 
   return 0;
 }
 
-int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
-  (void)request;
+static int op_apply_add(CeedOperator op, CeedVector in, CeedVector out) {
   Ceed ceed = op->ceed;
   if (op->composite) {
-    for (int i = 0; i < op->nsubs; i++) CeedChk(CeedOperatorApplyAdd(op->subs[i], in, out, request));
+    for (int i = 0; i < op->nsubs; i++) CeedChk(op_apply_add(op->subs[i], in, out));
     return 0;
   }
   if (op->kind == OP_UNSET) CeedChk(op_setup(op));
@@ -1460,10 +1470,15 @@ int CeedOperatorApplyPartitionedB200(CeedOperator op, CeedVector in, CeedVector 
 }
 
 /* libCEED interface semantics: zero every output (active and passive), then ApplyAdd */
-int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
+int CeedOperatorApplyAdd(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
+  (void)request;
+  CeedChk(op_apply_add(op, in, out));
+  return vec_write_through(out);
+}
+static int op_apply(CeedOperator op, CeedVector in, CeedVector out) {
   if (op->composite) {
     if (out && out != CEED_VECTOR_NONE) CeedChk(CeedVectorSetValue(out, 0.0));
-    for (int i = 0; i < op->nsubs; i++) CeedChk(CeedOperatorApplyAdd(op->subs[i], in, out, request));
+    for (int i = 0; i < op->nsubs; i++) CeedChk(op_apply_add(op->subs[i], in, out));
     return 0;
   }
   if (op->kind == OP_UNSET) CeedChk(op_setup(op));
@@ -1479,7 +1494,12 @@ int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out, CeedReques
     if (op->kind == OP_FUSED_RESIDUAL && i == 1) continue;
     CeedChk(CeedVectorSetValue(v, 0.0));
   }
-  return CeedOperatorApplyAdd(op, in, out, request);
+  return op_apply_add(op, in, out);
+}
+int CeedOperatorApply(CeedOperator op, CeedVector in, CeedVector out, CeedRequest *request) {
+  (void)request;
+  CeedChk(op_apply(op, in, out));
+  return vec_write_through(out);
 }
 
 int CeedOperatorLinearAssembleAddDiagonal(CeedOperator op, CeedVector assembled, CeedRequest *request) {

@@ -255,3 +255,33 @@ def test_partitioned_apply_without_a_halo_equals_apply_plus_mask():
         with pytest.raises(libceed.CeedError, match="n_interface"):
             op.apply_partitioned(xc, yc, 3, None, mask)          # not a multiple of the element-group size
         yc.take_array(); xc.take_array()
+
+
+def test_borrowed_host_output_is_current_when_apply_returns():
+    """/cpu/self writes a CEED_USE_POINTER host array in place and the reference's ViewDiagnosticQuantities reads it
+    between CeedOperatorApply and CeedVectorTakeArray (misc.c:258-268): the borrowed host output must already hold the
+    result when CeedOperatorApply / CeedOperatorApplyAdd / CeedElemRestrictionGetMultiplicity return."""
+    import gpu_helpers as G
+    from ceedpetscsolid_b200 import ceed as libceed
+    g = G.GpuProblem("hyperSS", (3, 2, 2), 2)
+    g.residual()
+    fine = len(g.degrees) - 1
+    op = g.data[fine].opJacob
+    n = g.mesh.lsize(2)
+    x = np.random.default_rng(5).standard_normal(n)
+    y, y_ref = np.full(n, 7.0), np.empty(n)
+    xc, yc, rc = g.ceed.Vector(n), g.ceed.Vector(n), g.ceed.Vector(n)
+    xc.set_array(x, libceed.MEM_HOST, libceed.USE_POINTER)
+    rc.set_array(y_ref, libceed.MEM_HOST, libceed.USE_POINTER)
+    op.apply(xc, rc)
+    rc.take_array(libceed.MEM_HOST)
+    assert np.linalg.norm(y_ref) > 0
+    yc.set_array(y, libceed.MEM_HOST, libceed.USE_POINTER)
+    op.apply(xc, yc)
+    assert rel_err(y, y_ref) < 1e-14                 # before TakeArray
+    op.apply_add(xc, yc)
+    assert rel_err(y, 2 * y_ref) < 1e-14
+    g.data[fine].Erestrictu.get_multiplicity(yc)
+    assert y.min() >= 1.0 and y.max() <= 8.0 and np.all(y == np.round(y))
+    yc.take_array(libceed.MEM_HOST)
+    xc.take_array(libceed.MEM_HOST)
