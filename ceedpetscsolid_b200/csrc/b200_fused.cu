@@ -713,11 +713,171 @@ k_fused_diag(const __grid_constant__ DiagMats<P, Q> dm, const __grid_constant__ 
 // -----------------------------------------------------------------------------------
 template <int PC, int PF> struct XferMats { double J[PF * PC]; };
 
+// Shared memory of the transfer kernel: two lattices of three components per element (6 SC), element stride padded
+// like Cfg<Q>::SE.  The L-vector is touched only by two flat sweeps in L-vector order, f = (element, node, component)
+// with the component fastest: consecutive lanes read / write consecutive interlaced dofs, so a warp's request covers
+// a few full sectors instead of 32 separate ones (the line owners of one warp belong to EB different elements).
+__host__ __device__ constexpr int xfer_se(int Q) {
+  return elems_per_block(Q) == 16 ? ((6 * apply_sc(Q, Q)) | 1)
+                                  : 6 * apply_sc(Q, Q) + ((16 / elems_per_block(Q) - (6 * apply_sc(Q, Q)) % 16) + 16) % 16;
+}
+
+#ifndef B200_XFER_LINE_IO
+// resident CTAs per SM asked of the compiler (measured, profiles/r2_transfer_ab.txt): the prolongation (few loads,
+// many stores) gains from 8 (64 registers at PF = 5); the restriction onto PF = 5 keeps its 12 offset -> value ->
+// multiplicity load chains in flight only with the default allocation (a 64-register cap spills), below that 8 wins
+#ifndef B200_XFER_MIN_CTAS_PROLONG
+#define B200_XFER_MIN_CTAS_PROLONG 8
+#endif
+#ifndef B200_XFER_MIN_CTAS_RESTRICT
+#define B200_XFER_MIN_CTAS_RESTRICT(PF) ((PF) <= 3 ? 8 : 1)
+#endif
+template <int PC, int PF, int TR>
+__global__ void __launch_bounds__(Cfg<PF>::NT, TR ? B200_XFER_MIN_CTAS_RESTRICT(PF) : B200_XFER_MIN_CTAS_PROLONG)
+k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__restrict__ offc,
+           const int *__restrict__ offf, const double *__restrict__ mult, int inject, const double *__restrict__ in,
+           double *__restrict__ out, double *__restrict__ evec, const unsigned short *__restrict__ gtab) {
+  constexpr int Q = PF;  // lattice extent used for smem indexing
+  constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, NT = Cfg<Q>::NT, SE = xfer_se(Q);
+  constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
+  constexpr int NI = TR ? PF : PC, NO = TR ? PC : PF;  // line extents in / out
+  constexpr int NI3 = NI * NI * NI, NO3 = NO * NO * NO;
+  static_assert(3 * NO3 <= 3 * SC, "interlaced nodal output must fit in the first lattice triple");
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x, blk = blockIdx.x;
+  const int t = tid / EB, eb = tid - t * EB, a = t % Q, b = t / Q;
+  const int rem = nelem - blk * EB;
+  const int ebn = rem < EB ? rem : EB;
+  const bool act = t < T && eb < ebn;
+  double *R0 = smem + eb * SE, *R1 = R0 + 3 * SC;
+#define JM(o, i) (TR ? m.J[(i) * PC + (o)] : m.J[(o) * PC + (i)])
+  // ---- gather sweep: input nodes of the CTA's elements in L-vector order -> lattice R1 of each element
+  {
+    constexpr int NIT = (EB * 3 * NI3 + NT - 1) / NT;
+    const int total = ebn * 3 * NI3;
+    const int *oin = (TR ? offf : offc) + (size_t)blk * EB * NI3;
+    // every load is unconditional (index clamped into the CTA's range) so that the NIT dependent pairs
+    // offset -> value are all in flight together; only the shared-memory store is predicated
+    // the lattice word of each f is the same for every CTA: a small table instead of five divisions per entry
+    double v[NIT];
+    int o[NIT];
+    unsigned short w[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int f = tid + it * NT, fc = f < total ? f : total - 1;
+      const int node = fc / 3;  // runs over (element, node of the element)
+      o[it] = __ldg(oin + node) + (fc - node * 3);
+      w[it] = __ldg(gtab + fc);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) v[it] = __ldg(in + o[it]);
+    if (TR && mult) {
+#pragma unroll
+      for (int it = 0; it < NIT; it++) v[it] *= __ldg(mult + o[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+      const int f = tid + it * NT;
+      if (f < total) smem[w[it]] = v[it];
+    }
+  }
+  __syncthreads();
+  // ---- z-lines (a = i, b = j): contract z
+  if (act && a < NI && b < NI) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double l[NI];
+#pragma unroll
+      for (int k = 0; k < NI; k++) l[k] = R1[IDX(c, a, b, k)];
+#pragma unroll
+      for (int z = 0; z < NO; z++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NI; k++) s += JM(z, k) * l[k];
+        R0[IDX(c, a, b, z)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- y-lines (a = i < NI, b = z < NO)
+  if (act && a < NI && b < NO) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double l[NI];
+#pragma unroll
+      for (int j = 0; j < NI; j++) l[j] = R0[IDX(c, a, j, b)];
+#pragma unroll
+      for (int yy = 0; yy < NO; yy++) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < NI; j++) s += JM(yy, j) * l[j];
+        R1[IDX(c, a, yy, b)] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- x-lines (a = y < NO, b = z < NO) -> nodal output, interlaced [node][component], over lattice R0 (free now)
+  if (act && a < NO && b < NO) {
+    double *Rn = R0 + ((b * NO + a) * NO) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      double l[NI];
+#pragma unroll
+      for (int i = 0; i < NI; i++) l[i] = R1[IDX(c, i, a, b)];
+#pragma unroll
+      for (int xx = 0; xx < NO; xx++) {
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < NI; i++) s += JM(xx, i) * l[i];
+        Rn[xx * 3 + c] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- scatter sweep in L-vector order
+  {
+    constexpr int NIT = (EB * 3 * NO3 + NT - 1) / NT;
+    const int total = ebn * 3 * NO3;
+    const int *oout = (TR ? offc : offf) + (size_t)blk * EB * NO3;
+    double val[NIT];
+    int dst[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {  // unconditional loads (clamped), predicated stores: see the gather sweep
+      const int f = tid + it * NT, fc = f < total ? f : total - 1;
+      const int el = fc / (3 * NO3), node = fc / 3;
+      val[it] = smem[el * SE + (fc - el * 3 * NO3)];
+      dst[it] = __ldg(oout + node) + (fc - node * 3);
+    }
+    if (!TR && inject) {  // every element sharing the node stores the same interpolant
+#pragma unroll
+      for (int it = 0; it < NIT; it++)
+        if (tid + it * NT < total) out[dst[it]] = val[it];
+      return;
+    }
+    if (!TR && mult) {
+#pragma unroll
+      for (int it = 0; it < NIT; it++)
+        if (tid + it * NT < total) val[it] *= __ldg(mult + dst[it]);
+    }
+    if (evec) {  // deterministic mode: element outputs [e][node][comp], summed in a fixed order by the caller
+      double *ev = evec + (size_t)blk * EB * 3 * NO3;
+#pragma unroll
+      for (int it = 0; it < NIT; it++)
+        if (tid + it * NT < total) ev[tid + it * NT] = val[it];
+    } else {
+#pragma unroll
+      for (int it = 0; it < NIT; it++)
+        if (tid + it * NT < total) atomicAdd(out + dst[it], val[it]);
+    }
+  }
+#undef JM
+}
+#else  // B200_XFER_LINE_IO: the round-1 form, every line owner gathers and scatters its own nodes
 template <int PC, int PF, int TR>
 __global__ void __launch_bounds__(Cfg<PF>::NT)
 k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__restrict__ offc,
            const int *__restrict__ offf, const double *__restrict__ mult, int inject, const double *__restrict__ in,
-           double *__restrict__ out, double *__restrict__ evec) {
+           double *__restrict__ out, double *__restrict__ evec, const unsigned short *__restrict__) {
   constexpr int Q = PF;  // lattice extent used for smem indexing
   constexpr int T = Cfg<Q>::T, EB = Cfg<Q>::EB, SE = Cfg<Q>::SE;
   constexpr int SY = Cfg<Q>::SY, SZ = Cfg<Q>::SZ, SC = Cfg<Q>::SC;
@@ -799,6 +959,8 @@ k_transfer(const __grid_constant__ XferMats<PC, PF> m, int nelem, const int *__r
   }
 #undef JM
 }
+
+#endif  // B200_XFER_LINE_IO
 
 // -----------------------------------------------------------------------------------
 // host side
@@ -998,16 +1160,34 @@ static int launch_transfer(int nelem, const double *hJ, const int *offc, const i
   XferMats<PC, PF> m;
   for (int i = 0; i < PF * PC; i++) m.J[i] = hJ[i];
   auto kern = k_transfer<PC, PF, TR>;
+#ifndef B200_XFER_LINE_IO
+  constexpr size_t xfer_smem = (size_t)Cfg<PF>::EB * xfer_se(PF) * sizeof(double);
+#else
+  constexpr size_t xfer_smem = Cfg<PF>::SMEM;
+#endif
   static PerDevice pd;
   int dev;
   if (int rc = current_device(&dev)) return rc;
   if (!pd.configured[dev]) {
-    if (int rc = opt_in_smem(kern, Cfg<PF>::SMEM)) return rc;
+    if (int rc = opt_in_smem(kern, xfer_smem)) return rc;
+    // gather table: f = (el, node, c) with c fastest -> shared-memory word of lattice R1 of element el
+    constexpr int EB = Cfg<PF>::EB, NI = TR ? PF : PC, SC = Cfg<PF>::SC, SY = Cfg<PF>::SY, SZ = Cfg<PF>::SZ;
+    static_assert(EB * xfer_se(PF) < 65536, "gather table packing");
+    unsigned short h[EB * NI * NI * NI * 3];
+    for (int el = 0; el < EB; el++)
+      for (int z = 0; z < NI; z++)
+        for (int y = 0; y < NI; y++)
+          for (int x = 0; x < NI; x++)
+            for (int c = 0; c < 3; c++)
+              h[((el * NI * NI * NI) + (z * NI + y) * NI + x) * 3 + c] = (unsigned short)(el * xfer_se(PF) + 3 * SC + IDX(c, x, y, z));
+    B200_CHECK(cudaMalloc(&pd.table[dev], sizeof h));
+    B200_CHECK(cudaMemcpy(pd.table[dev], h, sizeof h, cudaMemcpyHostToDevice));
     pd.configured[dev] = true;
   }
   const int nblk = (nelem + Cfg<PF>::EB - 1) / Cfg<PF>::EB;
   if (nblk == 0) return 0;
-  kern<<<nblk, Cfg<PF>::NT, Cfg<PF>::SMEM, g_stream>>>(m, nelem, offc, offf, mult, inject, in, out, evec);
+  kern<<<nblk, Cfg<PF>::NT, xfer_smem, g_stream>>>(m, nelem, offc, offf, mult, inject, in, out, evec,
+                                                    static_cast<const unsigned short *>(pd.table[dev]));
   B200_LAUNCH_CHECK("k_transfer");
   return 0;
 }
