@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-2 multi-GPU pass: bash tools/run_r2_multi.sh N [quick]     (through gpurun --gpus N)
+# quick = only the default bench line the driver runs (no multi-GPU pytest, no exchange variants)
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
@@ -20,7 +21,8 @@ try:
 except Exception as e:
     print('bench line unreadable:', e); print(open('gpurun_out/r2m${N}_bench.json').read()[-2000:])
 PY
-# variants of the exchange, MatMult only
+# variants of the exchange, MatMult only (skipped in quick mode)
+if [ -n "$2" ]; then exit 0; fi
 VARIANTS=("--halo nccl" "--halo nccl --no-overlap" "--no-overlap" "")
 if [ "$N" -ge 4 ]; then VARIANTS=("--halo nccl --no-overlap" "--no-overlap" ""); fi
 for v in "${VARIANTS[@]}"; do
