@@ -11,62 +11,10 @@ Prolong_Ceed, Restrict_Ceed, ComputeStrainEnergy and ViewDiagnosticQuantities ar
 the vectors, runs the driver with host and with device memtype, and compares every output with the CPU oracle.
 """
 import os
-import subprocess
 
-import numpy as np
 import pytest
 
-from helpers import PHYS, OracleProblem, rel_err
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-TOL = 1e-12
-PROBLEM_ID = {"linElas": 0, "hyperSS": 1, "hyperFS": 2}
-
-
-def _closure(offsets, ncomp_stride, ncomp, bc_nodes=None):
-    """closure indices of every cell: interlaced dofs of each node in tensor order, essential-BC dofs as -(loc+1)"""
-    node = offsets // ncomp_stride                                               # (nelem, P^3)
-    loc = node[:, :, None] * ncomp + np.arange(ncomp)[None, None, :]
-    if bc_nodes is not None:
-        loc = np.where(bc_nodes[node][:, :, None], -(loc + 1), loc)
-    return np.ascontiguousarray(loc.reshape(offsets.shape[0], -1), dtype=np.int32)
-
-
-def _write_input(path, mesh, problem, degrees, memtype, u_fine, xs):
-    p = degrees[-1]
-    with open(path, "wb") as f:
-        def wi(*v):
-            np.asarray(v, dtype=np.int32).tofile(f)
-        wi(0x42323030, len(degrees), mesh.nelem, PROBLEM_ID[problem], memtype)
-        wi(*degrees)
-        xoff = mesh.offsets(1)
-        wi(mesh.lsize(1), mesh.lsize(1))
-        _closure(xoff, 3, 3).tofile(f)
-        np.ascontiguousarray(mesh.coord_lvector(), dtype=np.float64).tofile(f)
-        maps = []
-        for deg in degrees:
-            bc = mesh.boundary_mask(deg, "all")
-            free = ~np.repeat(bc, 3)
-            l2g = np.full(mesh.lsize(deg), -1, dtype=np.int32)
-            l2g[free] = np.arange(int(free.sum()), dtype=np.int32)
-            wi(mesh.lsize(deg), int(free.sum()))
-            _closure(mesh.offsets(deg), 3, 3, bc).tofile(f)
-            l2g.tofile(f)
-            maps.append(free)
-        nn = mesh.num_nodes(p)
-        wi(nn, nn)
-        _closure(mesh.offsets(p), 3, 1).tofile(f)
-        wi(8 * nn, 8 * nn)
-        _closure(mesh.offsets(p), 3, 8).tofile(f)
-        bc_idx = np.flatnonzero(~maps[-1]).astype(np.int32)
-        wi(bc_idx.size)
-        bc_idx.tofile(f)
-        np.ascontiguousarray(u_fine[bc_idx], dtype=np.float64).tofile(f)
-        np.ascontiguousarray(u_fine[maps[-1]], dtype=np.float64).tofile(f)
-        for x in xs:
-            np.ascontiguousarray(x, dtype=np.float64).tofile(f)
-    return maps
+from ref_host_code import DRIVER, ROOT, run_and_check
 
 
 @pytest.mark.gpu
@@ -77,58 +25,7 @@ def _write_input(path, mesh, problem, degrees, memtype, u_fine, xs):
 def test_reference_setup_and_matshell_callbacks_drive_the_backend(tmp_path, problem, n, degrees, memtype, resource):
     if not os.path.exists(DRIVER):
         pytest.skip("oracle/_ref/ref_driver not built (needs /root/reference at build time)")
-    from oracle import oracle
-    from test_gpu_postprocess import _oracle_post
-    p = degrees[-1]
-    o = OracleProblem(problem, n, p)
-    mesh = o.mesh
-    rng = np.random.default_rng(17)
-    frees = [~np.repeat(mesh.boundary_mask(deg, "all"), 3) for deg in degrees]
-    xs = [rng.standard_normal(int(fr.sum())) for fr in frees]
-    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
-    _write_input(inp, mesh, problem, degrees, memtype, o.u_fine, xs)
-    r = subprocess.run([DRIVER, inp, out, resource], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "ref_driver OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
-    res = np.fromfile(out, dtype=np.float64)
-    pos = 0
-
-    def take(k):
-        nonlocal pos
-        v = res[pos:pos + k]
-        pos += k
-        return v
-    # residual at the smooth state (boundary values inserted by the reference's FormResidual_Ceed at load 1)
-    assert rel_err(take(int(frees[-1].sum())), o.residual_fine(o.u_fine)[frees[-1]]) < TOL
-    locals_x = []
-    for l, deg in enumerate(degrees):
-        P = deg + 1
-        B, D, _, _ = oracle.basis_1d(P, o.Q, 0)
-        off, lsize = mesh.offsets(deg), mesh.lsize(deg)
-        xl = np.zeros(lsize)
-        xl[frees[l]] = xs[l]
-        locals_x.append(xl)
-        yo = oracle.operator_apply(problem, True, PHYS, o.nelem, P, o.Q, B, D, off, o.qdata, o.gradu, xl)
-        assert rel_err(take(xs[l].size), yo[frees[l]]) < TOL, ("jacobian", deg)
-        do = oracle.operator_diagonal(problem, PHYS, o.nelem, P, o.Q, B, D, off, o.qdata, o.gradu, lsize)
-        assert rel_err(take(xs[l].size), do[frees[l]]) < TOL, ("diagonal", deg)
-    for l in range(1, len(degrees)):
-        pc, pf = degrees[l - 1], degrees[l]
-        offc, offf, lc, lf = mesh.offsets(pc), mesh.offsets(pf), mesh.lsize(pc), mesh.lsize(pf)
-        mult = oracle.multiplicity(o.nelem, (pf + 1) ** 3, 3, lf, offf)
-        minv = np.where(frees[l], 1.0 / mult, 0.0)            # misc.c:115-143: L2G, G2L, reciprocal (0 stays 0)
-        yp = oracle.transfer(False, o.nelem, pc + 1, pf + 1, offc, offf, locals_x[l - 1], lf) * minv
-        assert rel_err(take(xs[l].size), yp[frees[l]]) < TOL, ("prolong", pf)
-        yr = oracle.transfer(True, o.nelem, pc + 1, pf + 1, offc, offf, locals_x[l] * minv, lc)
-        assert rel_err(take(xs[l - 1].size), yr[frees[l - 1]]) < TOL, ("restrict", pf)
-    e_ref, d_ref = _oracle_post(problem, mesh, p, o.u_fine)
-    energy = take(1)[0]
-    assert abs(energy - e_ref) < TOL * abs(e_ref)
-    # ViewDiagnosticQuantities (misc.c:217-300): (u, pressure, two strain invariants, volume ratio, energy density) per node
-    diag = take(8 * mesh.num_nodes(p)).reshape(-1, 8)
-    assert rel_err(diag[:, :3], o.u_fine.reshape(-1, 3)) < TOL
-    for k in range(3, 8):
-        assert rel_err(diag[:, k], d_ref[:, k]) < TOL, ("diagnostic", k)
-    assert pos == res.size
+    run_and_check(DRIVER, tmp_path, problem, n, degrees, memtype, resource)
 
 
 def test_driver_sources_exist_and_build_recipe_names_the_reference_files():
