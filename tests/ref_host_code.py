@@ -60,30 +60,41 @@ def write_input(path, mesh, problem, degrees, memtype, u_fine, xs):
     return maps
 
 
-def run_and_check(driver, tmp_path, problem, n, degrees, memtype, resource):
-    """run `driver` on a seeded case and compare everything it writes with the oracle (1e-12)"""
-    from oracle import oracle
-    from test_gpu_postprocess import _oracle_post
-    p = degrees[-1]
-    o = OracleProblem(problem, n, p)
-    mesh = o.mesh
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_host_code_golden.npz")
+GOLDEN_CASES = [("hyperFS", (3, 2, 2), [1, 2, 4]), ("hyperSS", (2, 2, 3), [1, 2, 3]), ("linElas", (3, 3, 2), [1, 2])]
+
+
+def case_key(problem, n, degrees):
+    return f"{problem}_n{'x'.join(map(str, n))}_p{'-'.join(map(str, degrees))}"
+
+
+def make_case(problem, n, degrees):
+    """the seeded case: (OracleProblem, free-dof mask of every level, global x vector of every level)"""
+    o = OracleProblem(problem, n, degrees[-1])
     rng = np.random.default_rng(17)
-    frees = [~np.repeat(mesh.boundary_mask(deg, "all"), 3) for deg in degrees]
+    frees = [~np.repeat(o.mesh.boundary_mask(deg, "all"), 3) for deg in degrees]
     xs = [rng.standard_normal(int(fr.sum())) for fr in frees]
+    return o, frees, xs
+
+
+def run_driver(driver, tmp_path, problem, n, degrees, memtype, resource):
+    """write the seeded case, run `driver` on it; returns (OracleProblem, free-dof masks, x vectors, raw output)"""
+    o, frees, xs = make_case(problem, n, degrees)
     inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
-    write_input(inp, mesh, problem, degrees, memtype, o.u_fine, xs)
+    write_input(inp, o.mesh, problem, degrees, memtype, o.u_fine, xs)
     r = subprocess.run([driver, inp, out, resource], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ref_driver OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
-    res = np.fromfile(out, dtype=np.float64)
-    pos = 0
+    return o, frees, xs, np.fromfile(out, dtype=np.float64)
 
-    def take(k):
-        nonlocal pos
-        v = res[pos:pos + k]
-        pos += k
-        return v
+
+def oracle_outputs(problem, degrees, o, frees, xs):
+    """what the driver writes, computed by the oracle from the mesh and the vectors alone: [(name, vector), ...] in the
+    driver's order"""
+    from oracle import oracle
+    from test_gpu_postprocess import _oracle_post
+    mesh, p = o.mesh, degrees[-1]
     # residual at the smooth state (boundary values inserted by the reference's FormResidual_Ceed at load 1)
-    assert rel_err(take(int(frees[-1].sum())), o.residual_fine(o.u_fine)[frees[-1]]) < TOL
+    parts = [("residual", o.residual_fine(o.u_fine)[frees[-1]])]
     locals_x = []
     for l, deg in enumerate(degrees):
         P = deg + 1
@@ -93,24 +104,59 @@ def run_and_check(driver, tmp_path, problem, n, degrees, memtype, resource):
         xl[frees[l]] = xs[l]
         locals_x.append(xl)
         yo = oracle.operator_apply(problem, True, PHYS, o.nelem, P, o.Q, B, D, off, o.qdata, o.gradu, xl)
-        assert rel_err(take(xs[l].size), yo[frees[l]]) < TOL, ("jacobian", deg)
+        parts.append((f"jacobian p={deg}", yo[frees[l]]))
         do = oracle.operator_diagonal(problem, PHYS, o.nelem, P, o.Q, B, D, off, o.qdata, o.gradu, lsize)
-        assert rel_err(take(xs[l].size), do[frees[l]]) < TOL, ("diagonal", deg)
+        parts.append((f"diagonal p={deg}", do[frees[l]]))
     for l in range(1, len(degrees)):
         pc, pf = degrees[l - 1], degrees[l]
         offc, offf, lc, lf = mesh.offsets(pc), mesh.offsets(pf), mesh.lsize(pc), mesh.lsize(pf)
         mult = oracle.multiplicity(o.nelem, (pf + 1) ** 3, 3, lf, offf)
         minv = np.where(frees[l], 1.0 / mult, 0.0)            # misc.c:115-143: L2G, G2L, reciprocal (0 stays 0)
         yp = oracle.transfer(False, o.nelem, pc + 1, pf + 1, offc, offf, locals_x[l - 1], lf) * minv
-        assert rel_err(take(xs[l].size), yp[frees[l]]) < TOL, ("prolong", pf)
+        parts.append((f"prolong {pc}->{pf}", yp[frees[l]]))
         yr = oracle.transfer(True, o.nelem, pc + 1, pf + 1, offc, offf, locals_x[l] * minv, lc)
-        assert rel_err(take(xs[l - 1].size), yr[frees[l - 1]]) < TOL, ("restrict", pf)
+        parts.append((f"restrict {pf}->{pc}", yr[frees[l - 1]]))
     e_ref, d_ref = _oracle_post(problem, mesh, p, o.u_fine)
-    energy = take(1)[0]
-    assert abs(energy - e_ref) < TOL * abs(e_ref)
+    parts.append(("strain energy", np.array([e_ref])))
     # ViewDiagnosticQuantities (misc.c:217-300): (u, pressure, two strain invariants, volume ratio, energy density) per node
-    diag = take(8 * mesh.num_nodes(p)).reshape(-1, 8)
-    assert rel_err(diag[:, :3], o.u_fine.reshape(-1, 3)) < TOL
-    for k in range(3, 8):
-        assert rel_err(diag[:, k], d_ref[:, k]) < TOL, ("diagnostic", k)
-    assert pos == res.size
+    diag = np.concatenate([o.u_fine.reshape(-1, 3), d_ref[:, 3:8]], axis=1)
+    for k in range(8):
+        parts.append((f"diagnostic column {k}", diag[:, k]))
+    return parts
+
+
+def split_like(res, parts, nnodes):
+    """cut the driver's raw output into the pieces of oracle_outputs (the diagnostic block is [node][8] in the file)"""
+    out, pos = [], 0
+    for name, v in parts:
+        if name.startswith("diagnostic column"):
+            k = int(name.split()[-1])
+            block = res[res.size - 8 * nnodes:].reshape(nnodes, 8)
+            out.append(block[:, k])
+            continue
+        out.append(res[pos:pos + v.size])
+        pos += v.size
+    assert pos + 8 * nnodes == res.size, "driver output has an unexpected length"
+    return out
+
+
+def check_against_golden(problem, n, degrees, res):
+    if not os.path.exists(GOLDEN):
+        return False
+    key = case_key(problem, n, degrees)
+    with np.load(GOLDEN) as g:
+        if key not in g.files:
+            return False
+        assert res.shape == g[key].shape and rel_err(res, g[key]) < TOL, ("golden", key)
+    return True
+
+
+def run_and_check(driver, tmp_path, problem, n, degrees, memtype, resource):
+    """run `driver` on a seeded case and compare everything it writes (1e-12) with the oracle and -- for the cases of
+    GOLDEN_CASES -- with the committed output of the reference's own host code and QFunctions on the CPU
+    (tests/golden/ref_host_code_golden.npz, generator tests/golden/make_ref_host_golden.py)"""
+    o, frees, xs, res = run_driver(driver, tmp_path, problem, n, degrees, memtype, resource)
+    check_against_golden(problem, n, degrees, res)
+    parts = oracle_outputs(problem, degrees, o, frees, xs)
+    for (name, want), got in zip(parts, split_like(res, parts, o.mesh.num_nodes(degrees[-1]))):
+        assert rel_err(got, want) < TOL, name

@@ -15,7 +15,7 @@ import os
 
 import pytest
 
-from ref_host_code import DRIVER_CPU, ROOT, run_and_check
+from ref_host_code import DRIVER_CPU, GOLDEN_CASES, ROOT, run_and_check
 
 
 @pytest.mark.parametrize("problem,n,degrees", [("hyperFS", (3, 2, 2), [1, 2, 4]), ("hyperSS", (2, 2, 3), [1, 2, 3]),
@@ -31,3 +31,18 @@ def test_cpu_driver_is_test_infrastructure_only():
     mk = open(os.path.join(ROOT, "ceedpetscsolid_b200", "csrc", "Makefile")).read()
     assert "ceed_cpu" not in mk and "oracle" not in mk
     assert open(os.path.join(ROOT, "oracle", "ceed_cpu.c")).read().startswith("/* TEST INFRASTRUCTURE ONLY")
+
+
+@pytest.mark.parametrize("problem,n,degrees", GOLDEN_CASES)
+def test_oracle_reproduces_the_committed_output_of_the_reference_host_code(problem, n, degrees):
+    """no driver, no reference tree: the oracle alone against tests/golden/ref_host_code_golden.npz, i.e. against what the
+    reference's set-up / MatShell functions and QFunctions produced on the CPU when the fixture was generated"""
+    import numpy as np
+    from helpers import rel_err
+    from ref_host_code import GOLDEN, case_key, make_case, oracle_outputs, split_like
+    o, frees, xs = make_case(problem, n, degrees)
+    parts = oracle_outputs(problem, degrees, o, frees, xs)
+    with np.load(GOLDEN) as g:
+        res = g[case_key(problem, n, degrees)]
+    for (name, want), got in zip(parts, split_like(res, parts, o.mesh.num_nodes(degrees[-1]))):
+        assert rel_err(got, want) < 1e-12, name
