@@ -10,6 +10,8 @@
  *   FormResidual_Ceed, ApplyJacobian_Ceed, GetDiag_Ceed,
  *   Prolong_Ceed, Restrict_Ceed, ComputeStrainEnergy                  matops.c:63-300
  *   ViewDiagnosticQuantities (its VecView captured instead of written) misc.c:217-300
+ *   optionally (forcing type in the second byte of the problem word): the forcing operator and, for MMS, the nodal
+ *   true solution that SetupLibceedFineLevel computes                  setuplibceed.c:550-640
  *
  * so the libCEED objects are created, wired and applied by the reference's code, the QFunction pointers are the
  * reference's own (which also exercises the backend's QFunction guard), and only the mesh (box, lexicographic
@@ -89,7 +91,9 @@ int main(int argc, char **argv) {
   fin = fopen(argv[1], "rb");
   if (!fin) { perror(argv[1]); return 1; }
   if (rd_i() != 0x42323030) { fprintf(stderr, "ref_driver: bad magic\n"); return 2; }
-  const int numLevels = rd_i(), nelem = rd_i(), problem = rd_i(), memtype = rd_i();
+  const int numLevels = rd_i(), nelem = rd_i(), problemWord = rd_i(), memtype = rd_i();
+  /* low byte: problemType; next byte: forcingType (0 = none, the default of the GPU test; elasticity.h:64-66) */
+  const int problem = problemWord & 0xff, forcing = (problemWord >> 8) & 0xff;
   const double nu = 0.3, E = 1.0;
   int *degrees = rd_iv((size_t)numLevels);
   const int fineLevel = numLevels - 1, device = memtype == CEED_MEM_DEVICE, ncompu = 3;
@@ -98,7 +102,8 @@ int main(int argc, char **argv) {
   AppCtx appCtx = (AppCtx)calloc(1, sizeof *appCtx);
   snprintf(appCtx->ceedResource, sizeof appCtx->ceedResource, "%s", resource);
   appCtx->problemChoice = (problemType)problem;
-  appCtx->forcingChoice = FORCE_NONE;
+  appCtx->forcingChoice = (forcingType)forcing;
+  appCtx->forcingVector[0] = 0.3; appCtx->forcingVector[1] = -1.0; appCtx->forcingVector[2] = 2.5;
   appCtx->multigridChoice = MULTIGRID_LOGARITHMIC;
   appCtx->degree = degrees[fineLevel];
   appCtx->qextra = 0;
@@ -137,8 +142,10 @@ int main(int argc, char **argv) {
   CeedQFunctionCreateIdentity(ceed, ncompu, CEED_EVAL_INTERP, CEED_EVAL_NONE, &qfProlong);
   CeedData *ceedData = (CeedData *)calloc((size_t)numLevels, sizeof(CeedData));
   for (int l = 0; l < numLevels; l++) ceedData[l] = (CeedData)calloc(1, sizeof **ceedData);
+  CeedVector forceCeed = NULL;       /* elasticity.c:289-294: the forcing L-vector, filled by the set-up */
+  if (forcing != FORCE_NONE) CeedVectorCreate(ceed, fine->lsize, &forceCeed);
   CHK(SetupLibceedFineLevel(fine, dmEnergy, dmDiagnostic, ceed, appCtx, phys, ceedData, fineLevel, ncompu, fine->gsize,
-                            fine->lsize, NULL, qfRestrict, qfProlong));
+                            fine->lsize, forceCeed, qfRestrict, qfProlong));
   for (int l = 0; l < numLevels; l++)
     CHK(SetupLibceedLevel(levelDMs[l], ceed, appCtx, phys, ceedData, l, ncompu, levelDMs[l]->gsize, levelDMs[l]->lsize, NULL,
                           qfRestrict, qfProlong));
@@ -216,6 +223,18 @@ int main(int argc, char **argv) {
     if (petsc_mini_viewed_n != dmDiagnostic->gsize) { fprintf(stderr, "ref_driver: diagnostic vector was not viewed\n"); return 5; }
     fwrite(petsc_mini_viewed, sizeof(double), (size_t)petsc_mini_viewed_n, fout);
     free(diagnosticCtx);
+  }
+  if (forcing != FORCE_NONE) { /* appended after everything else: the forcing L-vector and, for MMS, the nodal true solution */
+    const CeedScalar *f;
+    CeedVectorGetArrayRead(forceCeed, CEED_MEM_HOST, &f);
+    fwrite(f, sizeof(double), (size_t)fine->lsize, fout);
+    CeedVectorRestoreArrayRead(forceCeed, &f);
+    if (forcing == FORCE_MMS) {
+      CeedVectorGetArrayRead(ceedData[fineLevel]->truesoln, CEED_MEM_HOST, &f);
+      fwrite(f, sizeof(double), (size_t)fine->lsize, fout);
+      CeedVectorRestoreArrayRead(ceedData[fineLevel]->truesoln, &f);
+    }
+    CeedVectorDestroy(&forceCeed);
   }
   fclose(fout);
   fclose(fin);

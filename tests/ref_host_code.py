@@ -13,6 +13,8 @@ DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")            # against
 DRIVER_CPU = os.path.join(ROOT, "oracle", "_ref", "ref_driver_cpu")    # against oracle/ceed_cpu.c
 TOL = 1e-12
 PROBLEM_ID = {"linElas": 0, "hyperSS": 1, "hyperFS": 2}
+FORCING_ID = {0: 0, None: 0, "none": 0, "constant": 1, "mms": 2}      # elasticity.h:64-66
+FORCING_VECTOR = (0.3, -1.0, 2.5)                                      # tests/c/ref_driver.c
 
 
 def closure(offsets, ncomp_stride, ncomp, bc_nodes=None):
@@ -24,12 +26,12 @@ def closure(offsets, ncomp_stride, ncomp, bc_nodes=None):
     return np.ascontiguousarray(loc.reshape(offsets.shape[0], -1), dtype=np.int32)
 
 
-def write_input(path, mesh, problem, degrees, memtype, u_fine, xs):
+def write_input(path, mesh, problem, degrees, memtype, u_fine, xs, forcing=0):
     p = degrees[-1]
     with open(path, "wb") as f:
         def wi(*v):
             np.asarray(v, dtype=np.int32).tofile(f)
-        wi(0x42323030, len(degrees), mesh.nelem, PROBLEM_ID[problem], memtype)
+        wi(0x42323030, len(degrees), mesh.nelem, PROBLEM_ID[problem] | (FORCING_ID[forcing] << 8), memtype)
         wi(*degrees)
         xoff = mesh.offsets(1)
         wi(mesh.lsize(1), mesh.lsize(1))
@@ -77,17 +79,17 @@ def make_case(problem, n, degrees):
     return o, frees, xs
 
 
-def run_driver(driver, tmp_path, problem, n, degrees, memtype, resource):
+def run_driver(driver, tmp_path, problem, n, degrees, memtype, resource, forcing=0):
     """write the seeded case, run `driver` on it; returns (OracleProblem, free-dof masks, x vectors, raw output)"""
     o, frees, xs = make_case(problem, n, degrees)
     inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
-    write_input(inp, o.mesh, problem, degrees, memtype, o.u_fine, xs)
+    write_input(inp, o.mesh, problem, degrees, memtype, o.u_fine, xs, forcing)
     r = subprocess.run([driver, inp, out, resource], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ref_driver OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     return o, frees, xs, np.fromfile(out, dtype=np.float64)
 
 
-def oracle_outputs(problem, degrees, o, frees, xs):
+def oracle_outputs(problem, degrees, o, frees, xs, forcing=0):
     """what the driver writes, computed by the oracle from the mesh and the vectors alone: [(name, vector), ...] in the
     driver's order"""
     from oracle import oracle
@@ -122,21 +124,58 @@ def oracle_outputs(problem, degrees, o, frees, xs):
     diag = np.concatenate([o.u_fine.reshape(-1, 3), d_ref[:, 3:8]], axis=1)
     for k in range(8):
         parts.append((f"diagnostic column {k}", diag[:, k]))
+    if FORCING_ID[forcing]:
+        parts += forcing_outputs(o, p, forcing)
+    return parts
+
+
+def forcing_outputs(o, p, forcing):
+    """the forcing L-vector (setuplibceed.c:550-583: x INTERP, qdata, force INTERP^T) and, for MMS, the nodal true
+    solution averaged over the elements sharing a node (setuplibceed.c:585-640), from oracle pieces"""
+    import ctypes as C
+    from oracle import oracle
+    mesh, nel, P, Q = o.mesh, o.nelem, p + 1, o.Q
+    which = oracle.default_which()
+    Bx, Dx, _, qw = oracle.basis_1d(2, Q, 0)
+    Bu, Du, _, _ = oracle.basis_1d(P, Q, 0)
+    xe = mesh.coord_lvector()[mesh.offsets(1)[:, None, :] + np.arange(3)[None, :, None]]          # (nel, 3, 8)
+    xq = oracle.basis_apply(nel, 3, 2, Q, Bx, Dx, qw, 0, 1, xe).reshape(nel, 3, Q ** 3)
+    ctx = oracle.Physics(*PHYS) if forcing == "mms" else (C.c_double * 3)(*FORCING_VECTOR)
+    name = "SetupMMSForce" if forcing == "mms" else "SetupConstantForce"
+    fq = np.zeros((nel, 3, Q ** 3))
+    for e in range(nel):
+        (fq[e],) = oracle.call_qf(name, which, ctx, Q ** 3, [xq[e], o.qdata[e]], [3])
+    fe = oracle.basis_apply(nel, 3, P, Q, Bu, Du, qw, 1, 1, fq.reshape(nel, -1))
+    idx = (mesh.offsets(p)[:, None, :] + np.arange(3)[None, :, None]).reshape(-1)
+    force = np.zeros(mesh.lsize(p))
+    np.add.at(force, idx, fe.reshape(-1))
+    parts = [("forcing L-vector", force)]
+    if forcing == "mms":
+        Bt, Dt, _, qwt = oracle.basis_1d(2, P, 1)                                                 # vertices -> GLL nodes
+        xn = oracle.basis_apply(nel, 3, 2, P, Bt, Dt, qwt, 0, 1, xe).reshape(nel, 3, P ** 3)
+        te = np.zeros((nel, 3, P ** 3))
+        for e in range(nel):
+            (te[e],) = oracle.call_qf("MMSTrueSoln", which, None, P ** 3, [xn[e]], [3])
+        true = np.zeros(mesh.lsize(p))
+        np.add.at(true, idx, te.reshape(-1))
+        true /= oracle.multiplicity(nel, P ** 3, 3, mesh.lsize(p), mesh.offsets(p))
+        parts.append(("nodal true solution", true))
     return parts
 
 
 def split_like(res, parts, nnodes):
     """cut the driver's raw output into the pieces of oracle_outputs (the diagnostic block is [node][8] in the file)"""
-    out, pos = [], 0
+    out, pos, block = [], 0, None
     for name, v in parts:
         if name.startswith("diagnostic column"):
-            k = int(name.split()[-1])
-            block = res[res.size - 8 * nnodes:].reshape(nnodes, 8)
-            out.append(block[:, k])
+            if block is None:
+                block = res[pos:pos + 8 * nnodes].reshape(nnodes, 8)
+                pos += 8 * nnodes
+            out.append(block[:, int(name.split()[-1])])
             continue
         out.append(res[pos:pos + v.size])
         pos += v.size
-    assert pos + 8 * nnodes == res.size, "driver output has an unexpected length"
+    assert pos == res.size, "driver output has an unexpected length"
     return out
 
 
@@ -151,12 +190,13 @@ def check_against_golden(problem, n, degrees, res):
     return True
 
 
-def run_and_check(driver, tmp_path, problem, n, degrees, memtype, resource):
+def run_and_check(driver, tmp_path, problem, n, degrees, memtype, resource, forcing=0):
     """run `driver` on a seeded case and compare everything it writes (1e-12) with the oracle and -- for the cases of
     GOLDEN_CASES -- with the committed output of the reference's own host code and QFunctions on the CPU
     (tests/golden/ref_host_code_golden.npz, generator tests/golden/make_ref_host_golden.py)"""
-    o, frees, xs, res = run_driver(driver, tmp_path, problem, n, degrees, memtype, resource)
-    check_against_golden(problem, n, degrees, res)
-    parts = oracle_outputs(problem, degrees, o, frees, xs)
+    o, frees, xs, res = run_driver(driver, tmp_path, problem, n, degrees, memtype, resource, forcing)
+    if not FORCING_ID[forcing]:
+        check_against_golden(problem, n, degrees, res)
+    parts = oracle_outputs(problem, degrees, o, frees, xs, forcing)
     for (name, want), got in zip(parts, split_like(res, parts, o.mesh.num_nodes(degrees[-1]))):
         assert rel_err(got, want) < TOL, name

@@ -26,6 +26,18 @@ def test_reference_host_code_on_the_generic_cpu_restatement_equals_the_oracle(tm
     run_and_check(DRIVER_CPU, tmp_path, problem, n, degrees, 0, "/cpu/self")
 
 
+@pytest.mark.parametrize("problem,n,degrees,forcing", [("linElas", (3, 2, 2), [1, 2], "mms"), ("linElas", (2, 2, 2), [1, 3], "constant"),
+                                                       ("hyperFS", (2, 2, 2), [1, 2], "constant")])
+def test_reference_forcing_and_true_solution_setup_equal_the_oracle(tmp_path, problem, n, degrees, forcing):
+    """-forcing constant / mms (setuplibceed.c:550-640): the reference's forcing operator (SetupConstantForce /
+    SetupMMSForce: x INTERP, qdata, force INTERP^T) and, for MMS, its nodal true solution (MMSTrueSoln on a P=2 -> GLL
+    basis, divided by the multiplicity through CeedVectorGetArray) on the generic CPU restatement, besides everything
+    the other cases check"""
+    if not os.path.exists(DRIVER_CPU):
+        pytest.skip("oracle/_ref/ref_driver_cpu not built (needs /root/reference at build time)")
+    run_and_check(DRIVER_CPU, tmp_path, problem, n, degrees, 0, "/cpu/self", forcing=forcing)
+
+
 def test_cpu_driver_is_test_infrastructure_only():
     """the generic CPU restatement lives under oracle/ and is linked into nothing the product ships"""
     mk = open(os.path.join(ROOT, "ceedpetscsolid_b200", "csrc", "Makefile")).read()
